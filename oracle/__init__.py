@@ -1,0 +1,306 @@
+"""CPU oracle for the NumbaCS flow-map + FTLE + LAVD hot path (ctypes front-end).
+
+THIS IS TEST INFRASTRUCTURE.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the product package
+``numbacs_b200`` never does.  The arithmetic lives in ``numbacs_oracle.c`` (see its header for
+the reference file:line map and for what is pinned / unpinned); this module only mirrors the
+reference's Python call signatures so that parity tests read like the reference's own tests:
+
+    get_predefined_flow   /root/reference/src/numbacs/flows.py:1104
+    get_interp_arrays_2D  flows.py:9      get_interp_arrays_scalar  flows.py:85
+    get_flow_2D           flows.py:121    get_callable_scalar(_linear)  flows.py:387, 601
+    flowmap / flowmap_n / flowmap_grid_2D / flowmap_n_grid_2D   integration.py:7, 64, 123, 467
+    ftle_grid_2D / lavd_grid_2D           diagnostics.py:21, 272
+    composite_simpsons                    utils.py:611
+"""
+import ctypes as C
+import os
+import subprocess
+from math import pi, sqrt
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libnumbacs_oracle.so")
+
+KINDS = {"double_gyre": 0, "bickley_jet": 1, "abc": 2, "spline2d": 3}
+EXTRAP = {"constant": 0, "linear": 1, "nearest": 2}
+
+
+def build(force=False):
+    """Compile the C restatement with gcc (seconds)."""
+    src = os.path.join(_HERE, "numbacs_oracle.c")
+    if (force or not os.path.exists(_SO)
+            or os.path.getmtime(_SO) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "-B"])
+    return _SO
+
+
+_lib = None
+_dp = C.POINTER(C.c_double)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_SO)
+        L.oracle_flow_new.restype = C.c_void_p
+        L.oracle_flow_new.argtypes = [C.c_int]
+        L.oracle_flow_new_spline.restype = C.c_void_p
+        L.oracle_flow_new_spline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_double]
+        L.oracle_scalar_new.restype = C.c_void_p
+        L.oracle_scalar_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.oracle_free.argtypes = [C.c_void_p]
+        L.oracle_rhs.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_eval_spline3.restype = C.c_double
+        L.oracle_eval_spline3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_eval_linear3.restype = C.c_double
+        L.oracle_eval_linear3.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double]
+        L.oracle_prefilter3.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]
+        L.oracle_flowmap_pts.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_int64,
+                                         C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]
+        L.oracle_flowmap_grid_2d.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                             C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                             C.c_double, C.c_double, C.c_void_p, C.c_int64, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
+        L.oracle_ftle_grid_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double,
+                                          C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_composite_simpsons.restype = C.c_double
+        L.oracle_composite_simpsons.argtypes = [C.c_void_p, C.c_int64, C.c_double]
+        L.oracle_lavd_grid_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
+                                          C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        _lib = L
+    return _lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+def set_num_threads(n):
+    lib().oracle_set_num_threads(int(n))
+
+
+class Flow:
+    """Owns a C flow_t; keeps borrowed coefficient arrays alive."""
+
+    def __init__(self, handle, ndim, keep=()):
+        self.handle = handle
+        self.ndim = ndim
+        self._keep = keep
+
+    def __del__(self):
+        try:
+            lib().oracle_free(self.handle)
+        except Exception:
+            pass
+
+    def rhs(self, t, y, p):
+        y = _f64(y)
+        p = _f64(p)
+        dy = np.zeros(self.ndim)
+        lib().oracle_rhs(self.handle, float(t), _ptr(y), _ptr(dy), _ptr(p))
+        return dy
+
+
+class Scalar:
+    def __init__(self, handle, linear, keep=()):
+        self.handle = handle
+        self.linear = linear
+        self._keep = keep
+
+    def __del__(self):
+        try:
+            lib().oracle_free(self.handle)
+        except Exception:
+            pass
+
+    def __call__(self, pts):
+        pts = np.atleast_2d(_f64(pts))
+        fn = lib().oracle_eval_linear3 if self.linear else lib().oracle_eval_spline3
+        return np.array([fn(self.handle, *map(float, q)) for q in pts])
+
+
+def default_params(flow_str, int_direction=1.0):
+    """Default parameter vectors and domains of get_predefined_flow (flows.py:1160-1172,
+    1215-1238, 1262-1273).  Note the reference forces int_direction=1 for bickley (1219)."""
+    if flow_str == "double_gyre":
+        return (np.array([int_direction, 0.1, 0.25, 0.0, 0.2 * pi, 0.0]), ((0.0, 2.0), (0.0, 1.0)))
+    if flow_str == "bickley_jet":
+        r_e = 6371.0e-3
+        U0 = 86400 * 62.66e-6
+        L = 1770.0e-3
+        k1, k2, k3 = 2.0 / r_e, 4.0 / r_e, 6.0 / r_e
+        c2 = 0.205 * U0
+        c3 = 0.461 * U0
+        c1 = c3 + (sqrt(5) - 1) * (c2 - c3)
+        return (np.array([1.0, U0, L, 0.0075, 0.15, 0.3, k1, k2, k3, c1, c2, c3]),
+                ((0.0, r_e * pi), (-3.0, 3.0)))
+    if flow_str == "abc":
+        return (np.array([int_direction, 3 ** 0.5, 2 ** 0.5, 1.0, 0.5]),
+                ((0.0, 2 * pi), (0.0, 2 * pi), (0.0, 2 * pi)))
+    raise ValueError(flow_str)
+
+
+def get_predefined_flow(flow_str, int_direction=1.0, return_default_params=True,
+                        return_domain=True):
+    f = Flow(lib().oracle_flow_new(KINDS[flow_str]), 3 if flow_str == "abc" else 2)
+    p, dom = default_params(flow_str, int_direction)
+    out = [f]
+    if return_default_params:
+        out.append(p)
+    if return_domain:
+        out.append(dom)
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def prefilter(data):
+    data = _f64(data)
+    n0, n1, n2 = data.shape
+    out = np.zeros((n0 + 2, n1 + 2, n2 + 2))
+    lib().oracle_prefilter3(_ptr(data), n0, n1, n2, _ptr(out))
+    return out
+
+
+def get_interp_arrays_2D(tvals, xvals, yvals, U, V):
+    nt, nx, ny = U.shape
+    grid = ((tvals[0], tvals[-1], nt), (xvals[0], xvals[-1], nx), (yvals[0], yvals[-1], ny))
+    return grid, prefilter(U), prefilter(V)
+
+
+def get_interp_arrays_scalar(tvals, xvals, yvals, f):
+    nt, nx, ny = f.shape
+    if tvals[1] < tvals[0]:
+        f = np.flip(f, axis=0)
+        tvals = tvals[::-1]
+    grid = ((tvals[0], tvals[-1], nt), (xvals[0], xvals[-1], nx), (yvals[0], yvals[-1], ny))
+    return grid, prefilter(f)
+
+
+def _grid9(grid):
+    return _f64(np.array([[g[0], g[1], float(g[2])] for g in grid]).ravel())
+
+
+def get_flow_2D(grid_vel, C_eval_u, C_eval_v, spherical=0, extrap_mode="constant", r=6371.0):
+    g = _grid9(grid_vel)
+    cu, cv = _f64(C_eval_u), _f64(C_eval_v)
+    h = lib().oracle_flow_new_spline(_ptr(g), _ptr(cu), _ptr(cv), int(spherical),
+                                     EXTRAP[extrap_mode], float(r))
+    return Flow(h, 2, keep=(g, cu, cv))
+
+
+def get_callable_scalar(grid_f, C_eval_f, extrap_mode="constant"):
+    g = _grid9(grid_f)
+    c = _f64(C_eval_f)
+    return Scalar(lib().oracle_scalar_new(_ptr(g), _ptr(c), EXTRAP[extrap_mode]), False, (g, c))
+
+
+def get_callable_scalar_linear(grid_f, f, extrap_mode="constant"):
+    g = _grid9(grid_f)
+    c = _f64(f)
+    return Scalar(lib().oracle_scalar_new(_ptr(g), _ptr(c), EXTRAP[extrap_mode]), True, (g, c))
+
+
+def _mask(mask):
+    if mask is None:
+        return None
+    return np.ascontiguousarray(mask, dtype=np.uint8)
+
+
+def flowmap_pts(flow, t0, T, pts, params, n=2, last_only=True, rtol=1e-6, atol=1e-8, mask=None,
+                full=False):
+    pts = _f64(pts)
+    params = _f64(params)
+    npts, nd = pts.shape
+    assert nd == flow.ndim
+    out = np.zeros((npts, nd) if last_only else (npts, n, nd))
+    tspan = np.zeros(n)
+    status = np.zeros(npts, np.int32)
+    steps = np.zeros((npts, 2), np.int32)
+    stats = np.zeros(3, np.int64)
+    m = _mask(mask)
+    lib().oracle_flowmap_pts(flow.handle, float(t0), float(T), _ptr(pts), npts, _ptr(params),
+                             float(rtol), float(atol), _ptr(m), n, int(last_only), _ptr(out),
+                             _ptr(tspan), _ptr(status), _ptr(steps), _ptr(stats))
+    if full:
+        return out, tspan, status, steps, stats
+    return out if last_only else (out, tspan)
+
+
+def flowmap(flow, t0, T, pts, params, method="dop853", rtol=1e-6, atol=1e-8, mask=None):
+    return flowmap_pts(flow, t0, T, pts, params, 2, True, rtol, atol, mask)
+
+
+def flowmap_n(flow, t0, T, pts, params, method="dop853", n=2, rtol=1e-6, atol=1e-8, mask=None):
+    return flowmap_pts(flow, t0, T, pts, params, n, False, rtol, atol, mask)
+
+
+def _grid(flow, t0, T, x, y, params, n, last_only, rtol, atol, mask, full):
+    x, y, params = _f64(x), _f64(y), _f64(params)
+    nx, ny = len(x), len(y)
+    out = np.zeros((nx, ny, 2) if last_only else (nx, ny, n, 2))
+    tspan = np.zeros(n)
+    status = np.zeros((nx, ny), np.int32)
+    steps = np.zeros((nx, ny, 2), np.int32)
+    stats = np.zeros(3, np.int64)
+    m = _mask(mask)
+    lib().oracle_flowmap_grid_2d(flow.handle, float(t0), float(T), _ptr(x), nx, _ptr(y), ny,
+                                 _ptr(params), float(rtol), float(atol), _ptr(m), n,
+                                 int(last_only), _ptr(out), _ptr(tspan), _ptr(status), _ptr(steps),
+                                 _ptr(stats))
+    if full:
+        return out, tspan, status, steps, stats
+    return out if last_only else (out, tspan)
+
+
+def flowmap_grid_2D(flow, t0, T, x, y, params, method="dop853", rtol=1e-6, atol=1e-8, mask=None,
+                    full=False):
+    return _grid(flow, t0, T, x, y, params, 2, True, rtol, atol, mask, full)
+
+
+def flowmap_n_grid_2D(flow, t0, T, x, y, params, n=50, method="dop853", rtol=1e-6, atol=1e-8,
+                      mask=None, full=False):
+    return _grid(flow, t0, T, x, y, params, n, False, rtol, atol, mask, full)
+
+
+def ftle_grid_2D(flowmap, T, dx, dy, mask=None):
+    fm = _f64(flowmap)
+    nx, ny = fm.shape[:2]
+    out = np.zeros((nx, ny))
+    m = _mask(mask)
+    lib().oracle_ftle_grid_2d(_ptr(fm), nx, ny, float(T), float(dx), float(dy), _ptr(m), _ptr(out))
+    return out
+
+
+def composite_simpsons(f, h):
+    f = _f64(f)
+    return lib().oracle_composite_simpsons(_ptr(f), len(f), float(h))
+
+
+def lavd_grid_2D(flowmap_n, tspan, T, vort_interp, xrav, yrav, period_x=0.0, period_y=0.0,
+                 mask=None):
+    fm = _f64(flowmap_n)
+    nx, ny, n = fm.shape[:3]
+    tspan, xrav, yrav = _f64(tspan), _f64(xrav), _f64(yrav)
+    out = np.zeros((nx, ny))
+    m = _mask(mask)
+    lib().oracle_lavd_grid_2d(_ptr(fm), nx, ny, n, _ptr(tspan), vort_interp.handle,
+                              int(vort_interp.linear), _ptr(xrav), _ptr(yrav), float(period_x),
+                              float(period_y), _ptr(m), _ptr(out))
+    return out
