@@ -1,0 +1,191 @@
+/*
+ * b200cs.h -- C-ABI of libb200cs.so: the B200-native flow-map + FTLE + LAVD hot path of NumbaCS.
+ *
+ * Every entry point below replaces one call the reference makes on this path (file:line are
+ * relative to the reference tree, alb3rtjarvis/numbacs v0.1.2).  The reference has no FFI of its
+ * own for this path -- it is Python calling numba-JIT loops that call the third-party
+ * `numbalsoda.dop853` and `interpolation.splines` -- so the boundary is drawn exactly where the
+ * reference's Python functions sit, and the ctypes binding in numbacs_b200/_lib.py (shown in
+ * INTEGRATION.md) is what a maintainer would add to the reference.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  All arrays float64, C-order, 'ij' indexing:
+ *     flowmap[i, j, :] belongs to (x[i], y[j]).
+ *   - every data pointer may be a HOST pointer or a DEVICE pointer (cudaPointerGetAttributes is
+ *     used to tell).  Host inputs are uploaded, host outputs are downloaded before the call
+ *     returns.  With device-only pointers the call is asynchronous on `stream`.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - work runs on the CURRENT CUDA device (cudaSetDevice by the caller; one process per GPU).
+ *   - return value: 0 = ok, < 0 = error (B200CS_E_*); b200cs_last_error() gives the message of
+ *     the calling thread's last failure.  No exceptions cross the ABI.
+ *   - ownership: the caller allocates every output; the library never frees caller memory.  Flow
+ *     and scalar-field handles own device copies of their coefficient arrays.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     B200CS_E_CUDA.
+ */
+#ifndef B200CS_H
+#define B200CS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CS_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define B200CS_API __attribute__((visibility("default")))
+#else
+#define B200CS_API
+#endif
+
+/* error codes */
+#define B200CS_OK 0
+#define B200CS_E_INVALID (-1)     /* bad argument */
+#define B200CS_E_CUDA (-2)        /* CUDA runtime error / no device */
+#define B200CS_E_HANDLE (-3)      /* unknown flow / scalar handle */
+#define B200CS_E_UNSUPPORTED (-4) /* e.g. method != dop853 */
+
+/* flow kinds: get_predefined_flow (src/numbacs/flows.py:1104-1295), get_flow_2D (flows.py:121-258) */
+#define B200CS_FLOW_DOUBLE_GYRE 0 /* flows.py:1146-1158, 6 params  */
+#define B200CS_FLOW_BICKLEY_JET 1 /* flows.py:1182-1213, 12 params */
+#define B200CS_FLOW_ABC 2         /* flows.py:1249-1258, 5 params, 3-D state */
+#define B200CS_FLOW_SPLINE2D 3    /* flows.py:156-253, 1 param (int_direction) */
+
+/* extrap_mode of interpolation.splines.eval_spline / eval_linear (flows.py:121, 387, 601) */
+#define B200CS_EXTRAP_CONSTANT 0
+#define B200CS_EXTRAP_LINEAR 1
+#define B200CS_EXTRAP_NEAREST 2
+
+/* `method` of flowmap* (src/numbacs/integration.py:8, 124).  Only DOP853 is implemented. */
+#define B200CS_METHOD_DOP853 0
+
+/* per-particle status written to the optional `status` arrays */
+#define B200CS_ST_MASKED 0     /* mask[i,j] true: not integrated, output row is 0 */
+#define B200CS_ST_OK 1         /* numbalsoda `success` == True */
+#define B200CS_ST_NMAX (-2)    /* more than 100000 steps */
+#define B200CS_ST_HSMALL (-3)  /* step size underflow */
+
+B200CS_API const char *b200cs_last_error(void);
+B200CS_API int b200cs_version(void);
+/* number of visible CUDA devices; B200CS_E_CUDA if none */
+B200CS_API int b200cs_device_count(int *out_count);
+
+/* ---- flow registry: replaces the `funcptr` (address of a numba @cfunc) the reference passes
+ *      around.  A GPU cannot call a CPU function pointer, so the int handle names a device-side
+ *      implementation instead. ------------------------------------------------------------ */
+
+/* get_predefined_flow(flow_str) -> funcptr               (flows.py:1104, returns 1286-1295) */
+B200CS_API int b200cs_flow_create_analytic(int kind, int *out_handle);
+
+/* get_flow_2D(grid_vel, C_eval_u, C_eval_v, spherical, extrap_mode, r) -> funcptr (flows.py:121)
+ * grid9 = {t0,t1,nt, x0,x1,nx, y0,y1,ny}; Cu/Cv are the (nt+2, nx+2, ny+2) prefilter outputs.
+ * The coefficients are copied (interleaved u,v) to the current device. */
+B200CS_API int b200cs_flow_create_spline(const double *grid9, const double *Cu, const double *Cv,
+                              int spherical, int extrap_mode, double r, int *out_handle);
+
+/* get_callable_scalar(grid_f, C_eval_f, extrap_mode)          (flows.py:387-415) linear = 0
+ * get_callable_scalar_linear(grid_f, f, extrap_mode)          (flows.py:601-636) linear = 1
+ * `data` is (nt+2, nx+2, ny+2) coefficients (cubic) or the raw (nt, nx, ny) field (linear). */
+B200CS_API int b200cs_scalar_create(const double *grid9, const double *data, int linear, int extrap_mode,
+                         int *out_handle);
+
+B200CS_API int b200cs_flow_destroy(int handle);   /* flows and scalar fields share one handle space */
+/* kind (B200CS_FLOW_* or -1 for a scalar field), state dimension, minimum length of params */
+B200CS_API int b200cs_flow_info(int handle, int *kind, int *ndim, int *min_params);
+
+/* get_interp_arrays_2D / get_interp_arrays_scalar: interpolation.splines.prefilter(grid, f, k=3)
+ * (flows.py:43-44, 116).  data (n0, n1, n2) -> coefs (n0+2, n1+2, n2+2), natural cubic B-spline. */
+B200CS_API int b200cs_prefilter_3d(const double *data, int64_t n0, int64_t n1, int64_t n2, double *coefs,
+                        void *stream);
+
+/* evaluate a scalar handle at npts points (t, x, y): get_callable_scalar(...)(pts) */
+B200CS_API int b200cs_scalar_eval(int handle, const double *pts /*[npts,3]*/, int64_t npts,
+                       double *out /*[npts]*/, void *stream);
+/* evaluate the RHS of a flow at npts states: dy = rhs(t[q], y[q,:], params)  (lsoda_sig cfunc) */
+B200CS_API int b200cs_flow_rhs(int flow, const double *t /*[npts]*/, const double *y /*[npts,ndim]*/,
+                    int64_t npts, const double *params, int nparams, double *dy /*[npts,ndim]*/,
+                    void *stream);
+
+/* ---- particle integration: numbalsoda.dop853 inside a prange over particles --------------- */
+
+/* flowmap_grid_2D(funcptr, t0, T, x, y, params, method, rtol, atol, mask)
+ *                                                    (integration.py:123-182)  n == 0
+ * flowmap_n_grid_2D(funcptr, t0, T, x, y, params, n, ...)   (integration.py:467-533)  n >= 2
+ *   out    : [nx, ny, 2]            if n == 0 (final position only)
+ *            [nx, ny, n, 2]         if n >= 2 (n output times incl. the initial condition)
+ *   tspan  : nullable [n] = params[0] * t_eval (integration.py:533)
+ *   mask   : nullable [nx, ny] bytes (numpy bool_); masked particles give zeros
+ *   status : nullable [nx, ny] int32 B200CS_ST_*
+ *   steps  : nullable [nx, ny, 2] int32 (accepted, rejected) step counts per particle
+ *   stats  : nullable [3] int64 = {sum nfev, sum accepted, sum rejected attempts}, accumulated
+ *            (+=) into the caller's buffer                                                     */
+B200CS_API int b200cs_flowmap_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
+                           const double *y, int64_t ny, const double *params, int nparams,
+                           int method, double rtol, double atol, const uint8_t *mask, int n,
+                           double *out, double *tspan, int32_t *status, int32_t *steps,
+                           int64_t *stats, void *stream);
+
+/* flowmap(funcptr, t0, T, pts, params, ...)       (integration.py:7-61)    n == 0 -> out[npts, ndim]
+ * flowmap_n(funcptr, t0, T, pts, params, n=, ...) (integration.py:64-120)  n >= 2 -> out[npts, n, ndim]
+ * pts is [npts, ndim]; ndim must equal the flow's state dimension (2, or 3 for abc). */
+B200CS_API int b200cs_flowmap_pts(int flow, double t0, double T, const double *pts, int64_t npts, int ndim,
+                       const double *params, int nparams, int method, double rtol, double atol,
+                       const uint8_t *mask, int n, double *out, double *tspan, int32_t *status,
+                       int32_t *steps, int64_t *stats, void *stream);
+
+/* ---- diagnostics -------------------------------------------------------------------------- */
+
+/* ftle_grid_2D(flowmap, T, dx, dy, mask)   (diagnostics.py:21-65; utils.py:9-46, 168-189) */
+B200CS_API int b200cs_ftle_grid_2d(const double *flowmap /*[nx,ny,2]*/, int64_t nx, int64_t ny, double T,
+                        double dx, double dy, const uint8_t *mask, double *ftle /*[nx,ny]*/,
+                        void *stream);
+
+/* ftle_grid_2D on a row slab of a larger grid (multi-GPU row blocks).  flowmap is [nx, ny, 2]
+ * INCLUDING halo rows: with halo_lo / halo_hi = 1 the first / last slab row only serves as the
+ * i-1 / i+1 stencil neighbour and no ftle row is produced for it; with 0 that edge is a true
+ * domain border (ftle = 0, diagnostics.py:52-53).  ftle is [nx - halo_lo - halo_hi, ny]; mask
+ * (nullable) is [nx, ny] like the slab. */
+B200CS_API int b200cs_ftle_slab_2d(const double *flowmap, int64_t nx, int64_t ny, double T, double dx,
+                        double dy, const uint8_t *mask, int halo_lo, int halo_hi, double *ftle,
+                        void *stream);
+
+/* The two calls of the README workflow in one: flowmap_grid_2D followed by ftle_grid_2D, with the
+ * flow map kept on the device in between.  `flowmap_out` is nullable (skip the 16 B/particle
+ * download when only the FTLE field is wanted).  ftle rows [row_lo, row_hi) of the FULL grid are
+ * produced for an x-slab x[0:nx] that already includes whatever halo rows the caller wants:
+ * with halo_lo / halo_hi = 1 the first / last slab row is integrated but only used as a stencil
+ * neighbour, and its ftle row is not written (multi-GPU row blocks); with 0 that edge is a true
+ * domain border and gets ftle = 0 like the reference.  ftle_out is [nx - halo_lo - halo_hi, ny]. */
+B200CS_API int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
+                                const double *y, int64_t ny, const double *params, int nparams,
+                                int method, double rtol, double atol, const uint8_t *mask,
+                                double dx, double dy, int halo_lo, int halo_hi,
+                                double *flowmap_out /*nullable [nx,ny,2]*/, double *ftle_out,
+                                int32_t *status, int64_t *stats, void *stream);
+
+/* lavd_grid_2D(flowmap_n, tspan, T, vort_interp, xrav, yrav, period_x, period_y, mask)
+ *                                          (diagnostics.py:272-379; utils.py:611-655)
+ * `vort` is a handle from b200cs_scalar_create.  vort_avg (nullable, [n]) returns the spatial
+ * means (diagnostics.py:324-331); with vort_avg_in != 0 it is read instead of computed (the
+ * multi-GPU path all-reduces it between two calls). */
+B200CS_API int b200cs_lavd_grid_2d(const double *flowmap_n /*[nx,ny,n,2]*/, int64_t nx, int64_t ny, int64_t n,
+                        const double *tspan /*[n]*/, int vort, const double *xrav,
+                        const double *yrav, int64_t nrav, double period_x, double period_y,
+                        const uint8_t *mask, double *vort_avg, int vort_avg_in,
+                        double *lavd /*[nx,ny]*/, void *stream);
+/* partial sums for the spatial mean: sums[k] = sum_q vort(tspan[k], xrav[q], yrav[q]) */
+B200CS_API int b200cs_lavd_vort_sums(int vort, const double *tspan, int64_t n, const double *xrav,
+                          const double *yrav, int64_t nrav, double *sums /*[n]*/, void *stream);
+
+/* ---- measurement helper -------------------------------------------------------------------- */
+
+/* register-resident DFMA chains on every SM for `iters` iterations; returns achieved FP64
+ * TFLOP/s (2 flops per DFMA) in *out_tflops.  Used as the measured FP64 roofline denominator. */
+B200CS_API int b200cs_fp64_peak(int iters, double *out_tflops, double *out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CS_H */

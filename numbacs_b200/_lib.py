@@ -1,0 +1,159 @@
+"""ctypes binding of libb200cs.so (the C-ABI declared in include/b200cs.h).
+
+This is the whole Python<->CUDA boundary: plain pointers and sizes.  numpy arrays are passed as
+host pointers (the library stages them), torch CUDA tensors as device pointers.  There is no CPU
+fallback: if the shared library has not been built, or no GPU is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200cs.so")
+
+E_INVALID, E_CUDA, E_HANDLE, E_UNSUPPORTED = -1, -2, -3, -4
+FLOW_KINDS = {"double_gyre": 0, "bickley_jet": 1, "abc": 2}
+EXTRAP = {"constant": 0, "linear": 1, "nearest": 2}
+METHOD_DOP853 = 0
+
+_vp, _i, _i64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_double
+_ip = C.POINTER(C.c_int)
+
+# name -> argtypes, exactly the prototypes of include/b200cs.h (restype is int unless noted)
+PROTOTYPES = {
+    "b200cs_version": [],
+    "b200cs_device_count": [_ip],
+    "b200cs_flow_create_analytic": [_i, _ip],
+    "b200cs_flow_create_spline": [_vp, _vp, _vp, _i, _i, _d, _ip],
+    "b200cs_scalar_create": [_vp, _vp, _i, _i, _ip],
+    "b200cs_flow_destroy": [_i],
+    "b200cs_flow_info": [_i, _ip, _ip, _ip],
+    "b200cs_prefilter_3d": [_vp, _i64, _i64, _i64, _vp, _vp],
+    "b200cs_scalar_eval": [_i, _vp, _i64, _vp, _vp],
+    "b200cs_flow_rhs": [_i, _vp, _vp, _i64, _vp, _i, _vp, _vp],
+    "b200cs_flowmap_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp, _i,
+                               _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200cs_flowmap_pts": [_i, _d, _d, _vp, _i64, _i, _vp, _i, _i, _d, _d, _vp, _i, _vp, _vp,
+                           _vp, _vp, _vp, _vp],
+    "b200cs_ftle_grid_2d": [_vp, _i64, _i64, _d, _d, _d, _vp, _vp, _vp],
+    "b200cs_ftle_slab_2d": [_vp, _i64, _i64, _d, _d, _d, _vp, _i, _i, _vp, _vp],
+    "b200cs_flowmap_ftle_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp,
+                                    _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "b200cs_lavd_grid_2d": [_vp, _i64, _i64, _i64, _vp, _i, _vp, _vp, _i64, _d, _d, _vp, _vp, _i,
+                            _vp, _vp],
+    "b200cs_lavd_vort_sums": [_i, _vp, _i64, _vp, _vp, _i64, _vp, _vp],
+    "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
+}
+
+_lib = None
+
+
+def load():
+    """Load libb200cs.so; raises if it has not been built (python -m numbacs_b200._build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build the CUDA library first "
+                "(python -m numbacs_b200._build, or __graft_entry__.build()). "
+                "numbacs_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.b200cs_last_error.restype = C.c_char_p
+        L.b200cs_last_error.argtypes = []
+        for name, argtypes in PROTOTYPES.items():
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = argtypes
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc == 0:
+        return
+    msg = load().b200cs_last_error().decode("utf-8", "replace")
+    if rc == E_HANDLE:
+        raise NotImplementedError(
+            msg + " -- numbacs_b200 integrates only flows created by its own get_predefined_flow / "
+            "get_flow_2D (device implementations); user-written numba cfuncs cannot run on the "
+            "GPU and there is no CPU fallback.")
+    if rc == E_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == E_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def _is_torch(a):
+    return type(a).__module__.split(".")[0] == "torch"
+
+
+class Arg:
+    """A marshalled array argument: .ptr for ctypes, keeps the backing object alive."""
+    __slots__ = ("obj", "ptr", "on_device")
+
+    def __init__(self, obj, ptr, on_device):
+        self.obj, self.ptr, self.on_device = obj, ptr, on_device
+
+
+def arg_in(a, dtype=np.float64):
+    """numpy / array-like -> host pointer; torch tensor -> its (host or device) pointer."""
+    if a is None:
+        return Arg(None, None, False)
+    if _is_torch(a):
+        import torch
+        tdt = {np.float64: torch.float64, np.uint8: torch.uint8, np.bool_: torch.bool}[dtype]
+        t = a
+        if dtype is np.uint8 and t.dtype == torch.bool:
+            t = t.view(torch.uint8) if t.is_contiguous() else t.contiguous().view(torch.uint8)
+        elif t.dtype != tdt:
+            t = t.to(tdt)
+        t = t.contiguous()
+        return Arg(t, C.c_void_p(t.data_ptr()), t.is_cuda)
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return Arg(arr, C.c_void_p(arr.ctypes.data), False)
+
+
+def mask_in(mask):
+    if mask is None:
+        return Arg(None, None, False)
+    if _is_torch(mask):
+        return arg_in(mask, np.uint8)
+    m = np.ascontiguousarray(mask)
+    if m.dtype != np.bool_ and m.dtype != np.uint8:
+        m = m.astype(np.bool_)
+    m = m.view(np.uint8)
+    return Arg(m, C.c_void_p(m.ctypes.data), False)
+
+
+def alloc_out(shape, dtype, device):
+    """Output buffer: numpy (host) or torch CUDA tensor (device)."""
+    if device:
+        import torch
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
+        t = torch.empty(shape, dtype=tdt, device="cuda")
+        return Arg(t, C.c_void_p(t.data_ptr()), True)
+    arr = np.empty(shape, dtype=dtype)
+    return Arg(arr, C.c_void_p(arr.ctypes.data), False)
+
+
+def current_stream(device):
+    """torch's current CUDA stream when tensors are involved, else the default stream."""
+    if device:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return None
+
+
+def device_count():
+    n = C.c_int(0)
+    check(load().b200cs_device_count(C.byref(n)))
+    return n.value
+
+
+def fp64_peak(iters=20000):
+    """Measured FP64 FMA peak of the current GPU in TFLOP/s (register-resident DFMA chains)."""
+    tf, ms = C.c_double(0.0), C.c_double(0.0)
+    check(load().b200cs_fp64_peak(int(iters), C.byref(tf), C.byref(ms)))
+    return tf.value, ms.value

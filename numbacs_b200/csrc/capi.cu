@@ -1,0 +1,526 @@
+// capi.cu -- the extern "C" boundary of libb200cs.so (declared in include/b200cs.h).
+// Host-side only: argument checking, host<->device staging, the flow registry, kernel launches.
+#include "common.cuh"
+#include "launch.cuh"
+
+namespace b200cs {
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+bool is_device_ptr(const void *p) {
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+// ---------------------------------------------------------------- registry
+static std::mutex g_reg_mu;
+static std::unordered_map<int, std::shared_ptr<FlowSpec>> g_reg;
+static int g_next_handle = 1000;  // never 0, never a plausible pointer
+
+int registry_add(std::shared_ptr<FlowSpec> f) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    const int h = g_next_handle++;
+    g_reg[h] = std::move(f);
+    return h;
+}
+
+std::shared_ptr<FlowSpec> registry_get(int handle) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    auto it = g_reg.find(handle);
+    if (it == g_reg.end()) {
+        set_error("unknown flow handle %d (only handles returned by b200cs_flow_create_* / "
+                  "b200cs_scalar_create are valid; a CPU cfunc address cannot run on the GPU)",
+                  handle);
+        throw Fail{B200CS_E_HANDLE};
+    }
+    return it->second;
+}
+
+bool registry_remove(int handle) {
+    std::lock_guard<std::mutex> lk(g_reg_mu);
+    return g_reg.erase(handle) > 0;
+}
+
+static void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (%s); libb200cs has no CPU fallback",
+                  e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        throw Fail{B200CS_E_CUDA};
+    }
+}
+
+static void read_grid9(const double *grid9, Axis3 &g) {
+    double h[9];
+    if (is_device_ptr(grid9)) B2_CHECK_CUDA(cudaMemcpy(h, grid9, sizeof(h), cudaMemcpyDeviceToHost));
+    else std::memcpy(h, grid9, sizeof(h));
+    for (int d = 0; d < 3; ++d) {
+        g.a[d] = h[3 * d];
+        g.b[d] = h[3 * d + 1];
+        g.n[d] = (int)h[3 * d + 2];
+        B2_REQUIRE(g.n[d] >= 2, "grid axis %d needs at least 2 points (got %d)", d, g.n[d]);
+        B2_REQUIRE(g.b[d] > g.a[d], "grid axis %d must be ascending", d);
+    }
+}
+
+// params are tiny: always read them on the host (they become kernel arguments)
+static void read_params(const double *params, int nparams, int min_params, RhsParams &R) {
+    B2_REQUIRE(params != nullptr && nparams >= min_params,
+               "params needs at least %d entries for this flow (got %d)", min_params, nparams);
+    B2_REQUIRE(nparams <= kMaxParams, "at most %d params supported (got %d)", kMaxParams, nparams);
+    for (int i = 0; i < kMaxParams; ++i) R.p[i] = 0.0;
+    if (is_device_ptr(params))
+        B2_CHECK_CUDA(cudaMemcpy(R.p, params, sizeof(double) * nparams, cudaMemcpyDeviceToHost));
+    else std::memcpy(R.p, params, sizeof(double) * nparams);
+}
+
+static void fill_rhs(const FlowSpec &f, RhsParams &R) {
+    R.coef_uv = nullptr;
+    R.r = f.r;
+    std::memset(&R.grid, 0, sizeof(R.grid));
+    if (f.kind == B200CS_FLOW_SPLINE2D) {
+        R.grid = make_grid_dev(f);
+        R.coef_uv = static_cast<const double2 *>(f.coef);
+    }
+}
+
+static void check_device(const FlowSpec &f) {
+    int dev = 0;
+    B2_CHECK_CUDA(cudaGetDevice(&dev));
+    B2_REQUIRE(f.coef == nullptr || f.device == dev,
+               "flow handle was created on device %d but the current device is %d", f.device, dev);
+}
+
+// common body of flowmap_grid_2d / flowmap_pts
+static void run_flowmap(int flow, double t0, double T, bool grid_mode, const double *x, int64_t nx,
+                        const double *y, int64_t ny, const double *pts, int64_t npts_in, int ndim,
+                        const double *params, int nparams, int method, double rtol, double atol,
+                        const uint8_t *mask, int n, double *out, double *tspan, int32_t *status,
+                        int32_t *steps, int64_t *stats, cudaStream_t s) {
+    require_device();
+    B2_REQUIRE(method == B200CS_METHOD_DOP853,
+               "only method='dop853' is implemented on the GPU (got method id %d)", method);
+    B2_REQUIRE(n == 0 || n >= 2, "n must be 0 (final state only) or >= 2 (got %d)", n);
+    B2_REQUIRE(rtol > 0.0 && atol >= 0.0, "rtol must be > 0 and atol >= 0");
+    auto f = registry_get(flow);
+    B2_REQUIRE(f->kind >= 0, "handle %d is a scalar field, not a flow", flow);
+    check_device(*f);
+    const long long npts = grid_mode ? (long long)nx * ny : (long long)npts_in;
+    B2_REQUIRE(npts >= 0, "negative particle count");
+    if (grid_mode) B2_REQUIRE(f->ndim == 2, "grid entry points need a 2-D flow");
+    else B2_REQUIRE(ndim == f->ndim, "pts has %d columns but the flow state is %d-D", ndim, f->ndim);
+
+    IntegArgs A{};
+    read_params(params, nparams, f->min_params, A.rhs);
+    fill_rhs(*f, A.rhs);
+    const double p0 = A.rhs.p[0];
+    A.x0 = p0 * t0;            // params[0] * linspace(t0, t0+T, n)[0]   (integration.py:164, 514)
+    A.xend = p0 * (t0 + T);    //                               ...[-1]
+    A.rtol = rtol;
+    A.atol = atol;
+    A.n_out = n;
+    A.out_p0 = p0;
+    A.out_t0 = t0;
+    A.out_step = (n > 1) ? ((t0 + T) - t0) / (double)(n - 1) : 0.0;  // numba linspace step
+    A.nx = nx;
+    A.ny = ny;
+    A.npts = npts;
+
+    if (tspan && n >= 2) {
+        // returned times are params[0] * t_eval (integration.py:120, 533)
+        std::vector<double> ts(n);
+        for (int k = 0; k < n; ++k) {
+            const double te = (k == n - 1) ? p0 * (t0 + T) : p0 * (t0 + (double)k * A.out_step);
+            ts[k] = p0 * te;
+        }
+        if (is_device_ptr(tspan))
+            B2_CHECK_CUDA(cudaMemcpyAsync(tspan, ts.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        else std::memcpy(tspan, ts.data(), sizeof(double) * n);
+        if (is_device_ptr(tspan)) B2_CHECK_CUDA(cudaStreamSynchronize(s));  // ts goes out of scope
+    }
+    if (npts == 0) return;
+
+    const int nd = f->ndim;
+    const size_t row = (n >= 2) ? (size_t)n * nd : (size_t)nd;
+    In<double> dx, dy, dpts;
+    if (grid_mode) {
+        B2_REQUIRE(x && y, "x and y must not be null");
+        dx = In<double>(x, nx, s);
+        dy = In<double>(y, ny, s);
+    } else {
+        B2_REQUIRE(pts, "pts must not be null");
+        dpts = In<double>(pts, (size_t)npts * nd, s);
+    }
+    In<uint8_t> dmask(mask, npts, s);
+    B2_REQUIRE(out, "out must not be null");
+    Out<double> dout(out, (size_t)npts * row, s);
+    Out<int32_t> dstatus(status, npts, s);
+    Out<int32_t> dsteps(steps, (size_t)npts * 2, s);
+    Out<int64_t> dstats(stats, 3, s, /*upload_first=*/true);
+
+    A.x = dx.dev;
+    A.y = dy.dev;
+    A.pts = dpts.dev;
+    A.mask = dmask.dev;
+    A.out = dout.dev;
+    A.out_aligned16 = ((reinterpret_cast<uintptr_t>(dout.dev) & 15) == 0) ? 1 : 0;
+    A.status = dstatus.dev;
+    A.steps = dsteps.dev;
+    A.stats = reinterpret_cast<unsigned long long *>(dstats.dev);
+
+    launch_flowmap(*f, A, grid_mode, s);
+
+    dout.download();
+    dstatus.download();
+    dsteps.download();
+    dstats.download();
+    if (dout.staged() || dstatus.staged() || dsteps.staged() || dstats.staged())
+        B2_CHECK_CUDA(cudaStreamSynchronize(s));
+}
+
+}  // namespace b200cs
+
+using namespace b200cs;
+
+extern "C" {
+
+const char *b200cs_last_error(void) { return g_err; }
+
+int b200cs_version(void) { return B200CS_VERSION; }
+
+int b200cs_device_count(int *out_count) {
+    return guarded([&] {
+        B2_REQUIRE(out_count, "out_count is null");
+        *out_count = 0;
+        require_device();
+        B2_CHECK_CUDA(cudaGetDeviceCount(out_count));
+    });
+}
+
+int b200cs_flow_create_analytic(int kind, int *out_handle) {
+    return guarded([&] {
+        B2_REQUIRE(out_handle, "out_handle is null");
+        auto f = std::make_shared<FlowSpec>();
+        f->kind = kind;
+        switch (kind) {
+        case B200CS_FLOW_DOUBLE_GYRE: f->ndim = 2; f->min_params = 6; break;
+        case B200CS_FLOW_BICKLEY_JET: f->ndim = 2; f->min_params = 12; break;
+        case B200CS_FLOW_ABC: f->ndim = 3; f->min_params = 5; break;
+        default:
+            set_error("unknown analytic flow kind %d", kind);
+            throw Fail{B200CS_E_INVALID};
+        }
+        *out_handle = registry_add(std::move(f));
+    });
+}
+
+int b200cs_flow_create_spline(const double *grid9, const double *Cu, const double *Cv, int spherical,
+                              int extrap_mode, double r, int *out_handle) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(grid9 && Cu && Cv && out_handle, "null argument");
+        B2_REQUIRE(spherical >= 0 && spherical <= 2, "spherical must be 0, 1 or 2 (got %d)", spherical);
+        B2_REQUIRE(extrap_mode >= 0 && extrap_mode <= 2, "unknown extrap_mode %d", extrap_mode);
+        auto f = std::make_shared<FlowSpec>();
+        f->kind = B200CS_FLOW_SPLINE2D;
+        f->ndim = 2;
+        f->min_params = 1;
+        f->spherical = spherical;
+        f->extrap = extrap_mode;
+        f->r = r;
+        read_grid9(grid9, f->grid);
+        B2_CHECK_CUDA(cudaGetDevice(&f->device));
+        const size_t count = (size_t)(f->grid.n[0] + 2) * (f->grid.n[1] + 2) * (f->grid.n[2] + 2);
+        f->coef_bytes = count * sizeof(double2);
+        B2_CHECK_CUDA(cudaMalloc(&f->coef, f->coef_bytes));
+        cudaStream_t s = nullptr;
+        {
+            In<double> du(Cu, count, s), dv(Cv, count, s);
+            launch_interleave(du.dev, dv.dev, (long long)count, static_cast<double2 *>(f->coef), s);
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
+        }
+        *out_handle = registry_add(std::move(f));
+    });
+}
+
+int b200cs_scalar_create(const double *grid9, const double *data, int linear, int extrap_mode,
+                         int *out_handle) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(grid9 && data && out_handle, "null argument");
+        B2_REQUIRE(extrap_mode >= 0 && extrap_mode <= 2, "unknown extrap_mode %d", extrap_mode);
+        auto f = std::make_shared<FlowSpec>();
+        f->kind = -1;
+        f->ndim = 0;
+        f->min_params = 0;
+        f->linear = linear ? 1 : 0;
+        f->extrap = extrap_mode;
+        read_grid9(grid9, f->grid);
+        B2_CHECK_CUDA(cudaGetDevice(&f->device));
+        const int pad = linear ? 0 : 2;
+        const size_t count = (size_t)(f->grid.n[0] + pad) * (f->grid.n[1] + pad) * (f->grid.n[2] + pad);
+        f->coef_bytes = count * sizeof(double);
+        B2_CHECK_CUDA(cudaMalloc(&f->coef, f->coef_bytes));
+        B2_CHECK_CUDA(cudaMemcpy(f->coef, data, f->coef_bytes, cudaMemcpyDefault));
+        *out_handle = registry_add(std::move(f));
+    });
+}
+
+int b200cs_flow_destroy(int handle) {
+    return guarded([&] {
+        if (!registry_remove(handle)) {
+            set_error("unknown flow handle %d", handle);
+            throw Fail{B200CS_E_HANDLE};
+        }
+    });
+}
+
+int b200cs_flow_info(int handle, int *kind, int *ndim, int *min_params) {
+    return guarded([&] {
+        auto f = registry_get(handle);
+        if (kind) *kind = f->kind;
+        if (ndim) *ndim = f->ndim;
+        if (min_params) *min_params = f->min_params;
+    });
+}
+
+int b200cs_prefilter_3d(const double *data, int64_t n0, int64_t n1, int64_t n2, double *coefs,
+                        void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(data && coefs, "null argument");
+        B2_REQUIRE(n0 >= 2 && n1 >= 2 && n2 >= 2, "every axis needs at least 2 points");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t nin = (size_t)n0 * n1 * n2, nout = (size_t)(n0 + 2) * (n1 + 2) * (n2 + 2);
+        In<double> din(data, nin, s);
+        Out<double> dout(coefs, nout, s);
+        launch_prefilter3(din.dev, n0, n1, n2, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_scalar_eval(int handle, const double *pts, int64_t npts, double *out, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(handle);
+        B2_REQUIRE(f->kind == -1, "handle %d is a flow, not a scalar field", handle);
+        check_device(*f);
+        B2_REQUIRE(pts && out, "null argument");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> dp(pts, (size_t)npts * 3, s);
+        Out<double> dout(out, npts, s);
+        launch_scalar_eval(*f, dp.dev, npts, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_flow_rhs(int flow, const double *t, const double *y, int64_t npts, const double *params,
+                    int nparams, double *dy, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(flow);
+        B2_REQUIRE(f->kind >= 0, "handle %d is a scalar field, not a flow", flow);
+        check_device(*f);
+        B2_REQUIRE(t && y && dy, "null argument");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        RhsParams R{};
+        read_params(params, nparams, f->min_params, R);
+        fill_rhs(*f, R);
+        In<double> dt(t, npts, s), dyin(y, (size_t)npts * f->ndim, s);
+        Out<double> dout(dy, (size_t)npts * f->ndim, s);
+        launch_rhs_eval(*f, R, dt.dev, dyin.dev, npts, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_flowmap_grid_2d(int flow, double t0, double T, const double *x, int64_t nx, const double *y,
+                           int64_t ny, const double *params, int nparams, int method, double rtol,
+                           double atol, const uint8_t *mask, int n, double *out, double *tspan,
+                           int32_t *status, int32_t *steps, int64_t *stats, void *stream) {
+    return guarded([&] {
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
+                    mask, n, out, tspan, status, steps, stats, static_cast<cudaStream_t>(stream));
+    });
+}
+
+int b200cs_flowmap_pts(int flow, double t0, double T, const double *pts, int64_t npts, int ndim,
+                       const double *params, int nparams, int method, double rtol, double atol,
+                       const uint8_t *mask, int n, double *out, double *tspan, int32_t *status,
+                       int32_t *steps, int64_t *stats, void *stream) {
+    return guarded([&] {
+        B2_REQUIRE(npts >= 0, "negative point count");
+        run_flowmap(flow, t0, T, false, nullptr, 0, nullptr, 0, pts, npts, ndim, params, nparams, method,
+                    rtol, atol, mask, n, out, tspan, status, steps, stats,
+                    static_cast<cudaStream_t>(stream));
+    });
+}
+
+int b200cs_ftle_grid_2d(const double *flowmap, int64_t nx, int64_t ny, double T, double dx, double dy,
+                        const uint8_t *mask, double *ftle, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmap && ftle, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE(T != 0.0 && dx != 0.0 && dy != 0.0, "T, dx and dy must be non-zero");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmap, np * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dout(ftle, np, s);
+        launch_ftle(dfm.dev, nx, ny, T, dx, dy, dmask.dev, dout.dev, 0, nx, true, true, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_ftle_slab_2d(const double *flowmap, int64_t nx, int64_t ny, double T, double dx, double dy,
+                        const uint8_t *mask, int halo_lo, int halo_hi, double *ftle, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmap && ftle, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE((halo_lo == 0 || halo_lo == 1) && (halo_hi == 0 || halo_hi == 1), "halo must be 0 or 1");
+        B2_REQUIRE(T != 0.0 && dx != 0.0 && dy != 0.0, "T, dx and dy must be non-zero");
+        const long long rows_out = (long long)nx - halo_lo - halo_hi;
+        B2_REQUIRE(rows_out >= 0, "slab smaller than its halo");
+        if (rows_out == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmap, np * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dout(ftle, (size_t)rows_out * ny, s);
+        launch_ftle(dfm.dev, nx, ny, T, dx, dy, dmask.dev, dout.dev, halo_lo, (long long)nx - halo_hi,
+                    halo_lo == 0, halo_hi == 0, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
+                                const double *y, int64_t ny, const double *params, int nparams,
+                                int method, double rtol, double atol, const uint8_t *mask, double dx,
+                                double dy, int halo_lo, int halo_hi, double *flowmap_out,
+                                double *ftle_out, int32_t *status, int64_t *stats, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(ftle_out, "ftle_out is null");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE((halo_lo == 0 || halo_lo == 1) && (halo_hi == 0 || halo_hi == 1), "halo must be 0 or 1");
+        B2_REQUIRE(T != 0.0 && dx != 0.0 && dy != 0.0, "T, dx and dy must be non-zero");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const long long rows_out = (long long)nx - halo_lo - halo_hi;
+        B2_REQUIRE(rows_out >= 0, "slab smaller than its halo");
+        if (nx == 0 || ny == 0) return;
+        const size_t np = (size_t)nx * ny;
+        // the flow map lives on the device between the two kernels; a host `flowmap_out` only
+        // receives a copy, a device `flowmap_out` is used directly
+        Scratch fm_tmp;
+        double *fm_dev = nullptr;
+        bool fm_host_copy = false;
+        if (flowmap_out && is_device_ptr(flowmap_out)) {
+            fm_dev = flowmap_out;
+        } else {
+            fm_tmp = Scratch(np * 2 * sizeof(double), s);
+            fm_dev = static_cast<double *>(fm_tmp.ptr);
+            fm_host_copy = flowmap_out != nullptr;
+        }
+        In<uint8_t> dmask(mask, np, s);  // staged once, used by both kernels
+        run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
+                    dmask.dev, 0, fm_dev, nullptr, status, nullptr, stats, s);
+        Out<double> dftle(ftle_out, (size_t)rows_out * ny, s);
+        launch_ftle(fm_dev, nx, ny, T, dx, dy, dmask.dev, dftle.dev, halo_lo, (long long)nx - halo_hi,
+                    halo_lo == 0, halo_hi == 0, s);
+        dftle.download();
+        if (fm_host_copy)
+            B2_CHECK_CUDA(cudaMemcpyAsync(flowmap_out, fm_dev, np * 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        if (dftle.staged() || fm_host_copy) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_lavd_vort_sums(int vort, const double *tspan, int64_t n, const double *xrav, const double *yrav,
+                          int64_t nrav, double *sums, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(vort);
+        B2_REQUIRE(f->kind == -1, "handle %d is a flow, not a scalar field", vort);
+        check_device(*f);
+        B2_REQUIRE(tspan && xrav && yrav && sums, "null argument");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> dts(tspan, n, s), dxr(xrav, nrav, s), dyr(yrav, nrav, s);
+        Out<double> dsum(sums, n, s);
+        launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, dsum.dev, s);
+        dsum.download();
+        if (dsum.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_lavd_grid_2d(const double *flowmap_n, int64_t nx, int64_t ny, int64_t n, const double *tspan,
+                        int vort, const double *xrav, const double *yrav, int64_t nrav, double period_x,
+                        double period_y, const uint8_t *mask, double *vort_avg, int vort_avg_in,
+                        double *lavd, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(vort);
+        B2_REQUIRE(f->kind == -1, "handle %d is a flow, not a scalar field", vort);
+        check_device(*f);
+        B2_REQUIRE(flowmap_n && tspan && lavd, "null argument");
+        B2_REQUIRE(n >= 3, "lavd needs at least 3 output times (got %lld)", (long long)n);
+        B2_REQUIRE(vort_avg_in ? vort_avg != nullptr : (xrav && yrav && nrav > 0),
+                   "either pass vort_avg (vort_avg_in=1) or the xrav/yrav grid");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        if (np == 0) return;
+        In<double> dfm(flowmap_n, np * n * 2, s), dts(tspan, n, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dlavd(lavd, np, s);
+        Out<double> davg(vort_avg, n, s, /*upload_first=*/vort_avg_in != 0);
+        Scratch avg_tmp;
+        double *avg_dev = davg.dev;
+        if (!avg_dev) {
+            avg_tmp = Scratch(sizeof(double) * n, s);
+            avg_dev = static_cast<double *>(avg_tmp.ptr);
+        }
+        if (!vort_avg_in) {
+            In<double> dxr(xrav, nrav, s), dyr(yrav, nrav, s);
+            launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, avg_dev, s);
+            launch_div_scalar(avg_dev, n, (double)nrav, s);  // np.mean
+        }
+        launch_lavd(*f, dfm.dev, (long long)np, n, dts.dev, avg_dev, period_x, period_y, dmask.dev,
+                    dlavd.dev, s);
+        dlavd.download();
+        if (!vort_avg_in) davg.download();
+        if (dlavd.staged() || davg.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_fp64_peak(int iters, double *out_tflops, double *out_ms) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(out_tflops && iters > 0, "bad argument");
+        double ms = 0.0;
+        run_fp64_peak(iters, out_tflops, &ms);
+        if (out_ms) *out_ms = ms;
+    });
+}
+
+}  // extern "C"

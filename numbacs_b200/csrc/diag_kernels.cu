@@ -1,0 +1,345 @@
+// diag_kernels.cu -- K3 (LAVD), K4 (cubic B-spline prefilter) and small utility kernels.
+//
+// LAVD replaces lavd_grid_2D (/root/reference/src/numbacs/diagnostics.py:272-379):
+//   (1) vort_avg[k] = mean over the initial grid of vort(tspan[k], x, y)   (324-331)
+//   (2) per particle: composite Simpson of |vort(traj(t_k), t_k) - vort_avg[k]|   (336-377),
+//       Simpson rule as in utils.py:611-655 (even number of intervals: 1/3 rule; odd: 1/3 rule on
+//       the first n-1 intervals plus the three-point end correction).
+// The prefilter replaces interpolation.splines.prefilter(grid, data, k=3) (flows.py:43-44, 116).
+#include "common.cuh"
+#include "launch.cuh"
+#include "spline.cuh"
+
+namespace b200cs {
+
+SplineGridDev make_grid_dev(const FlowSpec &f) {
+    SplineGridDev g{};
+    const int pad = f.linear ? 0 : 2;
+    for (int d = 0; d < 3; ++d) {
+        g.a[d] = f.grid.a[d];
+        g.b[d] = f.grid.b[d];
+        g.n[d] = f.grid.n[d];
+        g.delta[d] = (f.grid.b[d] - f.grid.a[d]) / (double)(f.grid.n[d] - 1);
+        g.inv_delta[d] = 1.0 / g.delta[d];
+    }
+    g.s1 = f.grid.n[2] + pad;
+    g.s0 = (long long)(f.grid.n[1] + pad) * g.s1;
+    g.extrap = f.extrap;
+    return g;
+}
+
+namespace {
+
+struct ScalarDev {
+    SplineGridDev g;
+    const double *C;
+    int linear;
+};
+
+__device__ __forceinline__ double scalar_at(const ScalarDev &S, double t, double x, double y) {
+    return S.linear ? eval_linear_s(S.g, S.C, t, x, y) : eval_spline_s(S.g, S.C, t, x, y);
+}
+
+__device__ __forceinline__ double pymod_any(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+    return r;
+}
+
+__global__ void scalar_eval_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ pts,
+                                   long long npts, double *__restrict__ out) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    out[q] = scalar_at(S, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
+}
+
+constexpr int kRedThreads = 256;
+
+// partial[k * gridDim.x + b] = sum over the block's strided share of the points
+__global__ void __launch_bounds__(kRedThreads)
+vort_partial_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ tspan,
+                    const double *__restrict__ xr, const double *__restrict__ yr, long long nrav,
+                    double *__restrict__ partial) {
+    __shared__ double red[kRedThreads / 32];
+    const int k = blockIdx.y;
+    const double t = tspan[k];
+    double acc = 0.0;
+    for (long long q = (long long)blockIdx.x * kRedThreads + threadIdx.x; q < nrav;
+         q += (long long)gridDim.x * kRedThreads)
+        acc += scalar_at(S, t, xr[q], yr[q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kRedThreads / 32; ++w) s += red[w];
+        partial[(long long)k * gridDim.x + blockIdx.x] = s;
+    }
+}
+
+// sums[k] = sum_b partial[k, b]  in a fixed order (deterministic)
+__global__ void vort_final_kernel(const double *__restrict__ partial, int nb, long long n,
+                                  double *__restrict__ sums) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double s = 0.0;
+    for (int b = 0; b < nb; ++b) s += partial[k * nb + b];
+    sums[k] = s;
+}
+
+__global__ void __launch_bounds__(128)
+lavd_kernel(const __grid_constant__ ScalarDev S, const double2 *__restrict__ fm_n, long long npts,
+            long long n, const double *__restrict__ tspan, const double *__restrict__ vavg,
+            double period_x, double period_y, const uint8_t *__restrict__ mask, double *__restrict__ lavd) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    if (mask != nullptr && mask[q]) {
+        lavd[q] = 0.0;
+        return;
+    }
+    const double2 *traj = fm_n + q * n;
+    auto integrand = [&](long long k) {
+        double2 p = __ldg(traj + k);
+        if (period_x != 0.0) p.x = pymod_any(p.x, period_x);
+        if (period_y != 0.0) p.y = pymod_any(p.y, period_y);
+        return fabs(scalar_at(S, __ldg(tspan + k), p.x, p.y) - __ldg(vavg + k));
+    };
+    const double h = fabs(tspan[1] - tspan[0]);
+    long long m = n - 1;  // number of intervals
+    double val;
+    if (m % 2 == 0) {
+        val = integrand(0);
+        val += integrand(m);
+        for (long long k = 1; k < m; ++k) val += ((k & 1) ? 4.0 : 2.0) * integrand(k);
+        val *= h / 3.0;
+    } else {
+        // Simpson 1/3 on the first m-1 intervals + three-point correction for the last one
+        const double f1 = integrand(n - 1), f2 = integrand(n - 2), f3 = integrand(n - 3);
+        m -= 1;
+        val = integrand(0);
+        val += f2;
+        for (long long k = 1; k < m; ++k) val += ((k & 1) ? 4.0 : 2.0) * integrand(k);
+        val *= h / 3.0;
+        val += (5.0 * h / 12.0) * f1 + (2.0 * h / 3.0) * f2 - (h / 12.0) * f3;
+    }
+    lavd[q] = val;
+}
+
+// ---- prefilter ------------------------------------------------------------------------------
+// One thread solves one line of the natural-BC (1,4,1) system along `axis` by the Thomas
+// algorithm, reading the data values from the interior of `c` (already shifted by +1 along the
+// axes processed so far) and writing the n+2 coefficients in place.  For axes 0 and 1 consecutive
+// threads walk consecutive y-positions, so every load/store is coalesced; axis 2 lines are
+// contiguous per thread and go through L1.
+// The elimination factors of the constant (1,4,1) matrix do not depend on the data: cp[k] is the
+// k-th iterate of x -> 1/(4 - x) from 1/4 and reaches its floating-point fixed point within 32
+// steps, so a 64-entry table in constant memory serves every line.
+__constant__ double kThomasCp[64];
+
+__global__ void prefilter_axis_kernel(double *__restrict__ c, long long n_lines, long long n,
+                                      long long line_stride_outer, long long line_count_inner,
+                                      long long line_stride_inner, long long stride) {
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lines) return;
+    const long long lo = l / line_count_inner, li = l - lo * line_count_inner;
+    double *p = c + lo * line_stride_outer + li * line_stride_inner;  // p[k*stride], k = 0..n+1
+    // data d[k] lives at p[(k+1)*stride]
+    const double d0 = p[stride], dl = p[n * stride];
+    if (n > 2) {
+        const long long m = n - 2;
+        // forward sweep: dp[k] stored in place of d[k+1] (position k+2)
+        double prev = 0.0;
+        for (long long k = 0; k < m; ++k) {
+            double rhs = 6.0 * p[(k + 2) * stride];
+            if (k == 0) rhs -= d0;
+            if (k == m - 1) rhs -= dl;
+            const double cpk = kThomasCp[k < 63 ? k : 63];
+            prev = (k == 0) ? rhs * cpk : (rhs - prev) * cpk;
+            p[(k + 2) * stride] = prev;
+        }
+        // back substitution: u[k+1] = dp[k] - cp[k] * u[k+2]
+        double next = p[(m + 1) * stride];
+        for (long long k = m - 2; k >= 0; --k) {
+            next = fma(-kThomasCp[k < 63 ? k : 63], next, p[(k + 2) * stride]);
+            p[(k + 2) * stride] = next;
+        }
+    }
+    p[0] = 2.0 * p[stride] - p[2 * stride];
+    p[(n + 1) * stride] = 2.0 * p[n * stride] - p[(n - 1) * stride];
+}
+
+// copies data[n0,n1,n2] into the interior of coefs[(n0+2),(n1+2),(n2+2)] and zeroes the shell
+__global__ void prefilter_embed_kernel(const double *__restrict__ data, long long n0, long long n1,
+                                       long long n2, double *__restrict__ c) {
+    const long long m1 = n1 + 2, m2 = n2 + 2;
+    const long long total = (n0 + 2) * m1 * m2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long i2 = idx % m2, r = idx / m2, i1 = r % m1, i0 = r / m1;
+        double v = 0.0;
+        if (i0 >= 1 && i0 <= n0 && i1 >= 1 && i1 <= n1 && i2 >= 1 && i2 <= n2)
+            v = data[((i0 - 1) * n1 + (i1 - 1)) * n2 + (i2 - 1)];
+        c[idx] = v;
+    }
+}
+
+__global__ void div_scalar_kernel(double *__restrict__ a, long long n, double d) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) a[k] = a[k] / d;
+}
+
+__global__ void interleave_kernel(const double *__restrict__ u, const double *__restrict__ v,
+                                  long long count, double2 *__restrict__ uv) {
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < count;
+         idx += (long long)gridDim.x * blockDim.x)
+        uv[idx] = make_double2(u[idx], v[idx]);
+}
+
+// ---- FP64 peak micro-benchmark: 16 independent register-resident DFMA chains per thread -------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, double *sink) {
+    double a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + i + threadIdx.x * 1e-3;
+    const double m = 0.9999999, b = 1.0e-7;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fma(a[i], m, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
+}
+
+ScalarDev make_scalar_dev(const FlowSpec &f) {
+    ScalarDev S{};
+    S.g = make_grid_dev(f);
+    S.C = static_cast<const double *>(f.coef);
+    S.linear = f.linear;
+    return S;
+}
+
+void init_thomas_table() {
+    // per-device upload: constant memory is per context/device, so redo it per device
+    static std::mutex mu;
+    static std::vector<int> done;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    for (int d : done)
+        if (d == dev) return;
+    double cp[64];
+    cp[0] = 1.0 / 4.0;
+    for (int k = 1; k < 64; ++k) cp[k] = 1.0 / (4.0 - cp[k - 1]);
+    B2_CHECK_CUDA(cudaMemcpyToSymbol(kThomasCp, cp, sizeof(cp)));
+    done.push_back(dev);
+}
+
+}  // namespace
+
+void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s) {
+    if (npts <= 0) return;
+    const ScalarDev S = make_scalar_dev(f);
+    scalar_eval_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, s>>>(S, pts, npts, out);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
+                      const double *yr, long long nrav, double *sums, cudaStream_t s) {
+    if (n <= 0) return;
+    B2_REQUIRE(n <= 65535, "too many output times for the LAVD mean (%lld)", n);
+    const ScalarDev S = make_scalar_dev(f);
+    long long nb = (nrav + kRedThreads - 1) / kRedThreads;
+    if (nb > 592) nb = 592;  // 4 blocks per SM on 148 SMs
+    if (nb < 1) nb = 1;
+    Scratch partial(sizeof(double) * n * nb, s);
+    vort_partial_kernel<<<dim3((unsigned)nb, (unsigned)n), kRedThreads, 0, s>>>(
+        S, tspan, xr, yr, nrav, static_cast<double *>(partial.ptr));
+    B2_CHECK_CUDA(cudaGetLastError());
+    vort_final_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(static_cast<double *>(partial.ptr),
+                                                                 (int)nb, n, sums);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_lavd(const FlowSpec &f, const double *fm_n, long long npts, long long n, const double *tspan,
+                 const double *vavg, double period_x, double period_y, const uint8_t *mask, double *lavd,
+                 cudaStream_t s) {
+    if (npts <= 0) return;
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(fm_n) & 15) == 0, "flowmap_n must be 16-byte aligned");
+    const ScalarDev S = make_scalar_dev(f);
+    lavd_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, s>>>(
+        S, reinterpret_cast<const double2 *>(fm_n), npts, n, tspan, vavg, period_x, period_y, mask, lavd);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_prefilter3(const double *data, long long n0, long long n1, long long n2, double *coefs,
+                       cudaStream_t s) {
+    init_thomas_table();
+    const long long m0 = n0 + 2, m1 = n1 + 2, m2 = n2 + 2;
+    (void)m0;
+    prefilter_embed_kernel<<<1184, 256, 0, s>>>(data, n0, n1, n2, coefs);
+    B2_CHECK_CUDA(cudaGetLastError());
+    const int tb = 128;
+    // axis 2: lines (i0 in 1..n0, i1 in 1..n1), contiguous
+    {
+        const long long lines = n0 * n1;
+        prefilter_axis_kernel<<<(unsigned)((lines + tb - 1) / tb), tb, 0, s>>>(
+            coefs + m1 * m2 + m2, lines, n2, m1 * m2, n1, m2, 1);
+        B2_CHECK_CUDA(cudaGetLastError());
+    }
+    // axis 1: lines (i0 in 1..n0, i2 in 0..m2-1), stride m2
+    {
+        const long long lines = n0 * m2;
+        prefilter_axis_kernel<<<(unsigned)((lines + tb - 1) / tb), tb, 0, s>>>(
+            coefs + m1 * m2, lines, n1, m1 * m2, m2, 1, m2);
+        B2_CHECK_CUDA(cudaGetLastError());
+    }
+    // axis 0: lines (i1 in 0..m1-1, i2 in 0..m2-1), stride m1*m2
+    {
+        const long long lines = m1 * m2;
+        prefilter_axis_kernel<<<(unsigned)((lines + tb - 1) / tb), tb, 0, s>>>(
+            coefs, lines, n0, 0, lines, 1, m1 * m2);
+        B2_CHECK_CUDA(cudaGetLastError());
+    }
+}
+
+void launch_div_scalar(double *a, long long n, double d, cudaStream_t s) {
+    if (n <= 0) return;
+    div_scalar_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a, n, d);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_interleave(const double *u, const double *v, long long count, double2 *uv, cudaStream_t s) {
+    interleave_kernel<<<1184, 256, 0, s>>>(u, v, count, uv);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void run_fp64_peak(int iters, double *tflops, double *ms) {
+    int dev = 0, sms = 0;
+    B2_CHECK_CUDA(cudaGetDevice(&dev));
+    B2_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    B2_CHECK_CUDA(cudaMalloc(&sink, sizeof(double)));
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    B2_CHECK_CUDA(cudaEventCreate(&e0));
+    B2_CHECK_CUDA(cudaEventCreate(&e1));
+    fp64_peak_kernel<<<blocks, threads>>>(iters / 8 + 1, 1.0, sink);  // warm-up
+    B2_CHECK_CUDA(cudaEventRecord(e0));
+    fp64_peak_kernel<<<blocks, threads>>>(iters, 1.0, sink);
+    B2_CHECK_CUDA(cudaEventRecord(e1));
+    B2_CHECK_CUDA(cudaEventSynchronize(e1));
+    float t = 0.f;
+    B2_CHECK_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    const double flops = 2.0 * 64.0 * (double)iters * (double)blocks * threads;
+    *tflops = flops / (t * 1e-3) / 1e12;
+    *ms = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+}
+
+}  // namespace b200cs

@@ -1,0 +1,265 @@
+// dop853.cuh -- one-thread-per-particle adaptive Dormand-Prince 8(5,3) integrator.
+//
+// Replaces numbalsoda.dop853(funcptr, u0, t_eval, rtol, atol, data) as called from
+// /root/reference/src/numbacs/integration.py:49, 108, 169, 520.  The step-size controller is
+// Hairer's classical one (dop853.f): safe 0.9, fac1 0.333, fac2 6, beta 0, facold 1e-4, hinit with
+// iord 8, "no growth after a reject", last step when x + 1.01 h passes xend; one continuous
+// integration over the output times with 7th-order dense output (contd8) at interior times.
+// Parity with the reference requires the SAME accept/reject sequence per particle, so nothing in
+// the controller is "improved".
+//
+// GPU shape: every lane owns its particle, its step size and its accept/reject decisions; one
+// loop iteration is one step ATTEMPT (12 stages, error estimate, predicated state update), so a
+// warp stays converged except for the FSAL evaluation of rejected lanes and the tail where lanes
+// need different numbers of attempts.  All tableau coefficients are compile-time constants (the
+// zero entries vanish); the stage slopes live in registers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <utility>
+
+#include "dop853_tableau.cuh"
+
+namespace b200cs {
+
+struct StepCounts {
+    int accepted = 0;
+    int rejected = 0;  // rejected attempts (including those before the first accepted step)
+    int dense = 0;     // accepted steps that needed the three extra dense-output stages
+};
+
+namespace detail {
+
+// err^(1/8) with three correctly rounded square roots (libm pow in the reference; the difference
+// is <= 1 ulp and only scales the next step size)
+__device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
+
+template <int S, int N, int... J>
+__device__ __forceinline__ void stage_arg(double (&yy)[N], const double (&y)[N], double h,
+                                          const double (&K)[17][N], std::integer_sequence<int, J...>) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double acc = 0.0;
+        // sum_j a(S,j) * K[j][i], j ascending, zero entries skipped at compile time
+        ((dop::a(S, J + 1) != 0.0 ? (void)(acc = fma(dop::kTab.a[S][J + 1], K[J + 1][i], acc)) : (void)0), ...);
+        yy[i] = fma(h, acc, y[i]);
+    }
+}
+
+template <int S, class Rhs, int N>
+__device__ __forceinline__ void do_stage(const Rhs &rhs, double x, double h, const double (&y)[N],
+                                         double (&K)[17][N]) {
+    double yy[N];
+    stage_arg<S, N>(yy, y, h, K, std::make_integer_sequence<int, S - 1>{});
+    rhs(fma(dop::kTab.c[S], h, x), yy, K[S]);
+}
+
+template <int R, int N, int... J>
+__device__ __forceinline__ double dense_row(const double (&K)[17][N], int i, std::integer_sequence<int, J...>) {
+    double acc = 0.0;
+    ((dop::d(R, J + 1) != 0.0 ? (void)(acc = fma(dop::kTab.d[R][J + 1], K[J + 1][i], acc)) : (void)0), ...);
+    return acc;
+}
+
+}  // namespace detail
+
+// Output sink for the n-time variant: called once per emitted row k (0 < k < n-1 via dense
+// output, k == n-1 with the end point; row 0 is written by the caller).
+template <int N>
+struct NoSink {
+    __device__ __forceinline__ void operator()(int, const double (&)[N]) const {}
+};
+
+// Integrates dy/ds = rhs(s, y) from s = x0 to s = xend.
+//   n_out  == 0 : only the final state is wanted (DENSE must be false)
+//   n_out  >= 2 : output times are t_k = p0 * (t0 + k*step), k = 0..n_out-1 (last = p0*(t0+T)),
+//                 rows 1..n_out-1 go to `sink`
+// Returns B200CS_ST_OK / _NMAX / _HSMALL; y holds the state reached.
+template <bool DENSE, class Rhs, int N, class Sink>
+__device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], double x0, double xend,
+                                                double rtol, double atol, int n_out, double out_p0,
+                                                double out_t0, double out_step, Sink &&sink,
+                                                StepCounts &cnt) {
+    constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
+    constexpr int kNmax = 100000;
+    double K[17][N];  // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages
+    double x = x0;
+    const double posneg = (xend - x0) < 0.0 ? -1.0 : 1.0;
+    const double hmax = fabs(xend - x0);
+    double facold = 1.0e-4;
+    bool last = false, reject = false;
+    int nstep = 0;
+    int iout = 1;  // next output row
+    // output time of row k, bit-identical to params[0]*np.linspace(t0, t0+T, n)[k]
+    auto t_out = [&](int k) { return __dmul_rn(out_p0, __dadd_rn(out_t0, __dmul_rn((double)k, out_step))); };
+    double tnext = 0.0;
+    if (DENSE) tnext = t_out(1);
+
+    rhs(x, y, K[1]);
+    // ---- hinit (iord = 8)
+    double h;
+    {
+        double dnf = 0.0, dny = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = fma(rtol, fabs(y[i]), atol);
+            const double a = K[1][i] / sk, b = y[i] / sk;
+            dnf = fma(a, a, dnf);
+            dny = fma(b, b, dny);
+        }
+        h = (dnf <= 1.0e-10 || dny <= 1.0e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
+        h = fmin(h, hmax) * posneg;
+        double y1[N], f1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = fma(h, K[1][i], y[i]);
+        rhs(x + h, y1, f1);
+        double der2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sk = fma(rtol, fabs(y[i]), atol);
+            const double a = (f1[i] - K[1][i]) / sk;
+            der2 = fma(a, a, der2);
+        }
+        der2 = sqrt(der2) / h;
+        const double der12 = fmax(fabs(der2), sqrt(dnf));
+        const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(h) * 1.0e-3)
+                                             : detail::pow_eighth(0.01 / der12);
+        h = fmin(100.0 * fabs(h), fmin(h1, hmax)) * posneg;
+    }
+
+    int status = B200CS_ST_OK;
+    for (;;) {
+        if (nstep > kNmax) { status = B200CS_ST_NMAX; break; }
+        if (0.1 * fabs(h) <= fabs(x) * kURound) { status = B200CS_ST_HSMALL; break; }
+        if ((x + 1.01 * h - xend) * posneg > 0.0) {
+            h = xend - x;
+            last = true;
+        }
+        ++nstep;
+        detail::do_stage<2>(rhs, x, h, y, K);
+        detail::do_stage<3>(rhs, x, h, y, K);
+        detail::do_stage<4>(rhs, x, h, y, K);
+        detail::do_stage<5>(rhs, x, h, y, K);
+        detail::do_stage<6>(rhs, x, h, y, K);
+        detail::do_stage<7>(rhs, x, h, y, K);
+        detail::do_stage<8>(rhs, x, h, y, K);
+        detail::do_stage<9>(rhs, x, h, y, K);
+        detail::do_stage<10>(rhs, x, h, y, K);
+        detail::do_stage<11>(rhs, x, h, y, K);
+        const double xph = x + h;
+        {   // stage 12 is evaluated at x + h exactly
+            double yy[N];
+            detail::stage_arg<12, N>(yy, y, h, K, std::make_integer_sequence<int, 11>{});
+            rhs(xph, yy, K[12]);
+        }
+        // 8th-order slope, candidate state, and the two embedded error estimates
+        double kb[N], y5[N];
+        double err = 0.0, err2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            double s = dop::kTab.b[1] * K[1][i];
+            s = fma(dop::kTab.b[6], K[6][i], s);
+            s = fma(dop::kTab.b[7], K[7][i], s);
+            s = fma(dop::kTab.b[8], K[8][i], s);
+            s = fma(dop::kTab.b[9], K[9][i], s);
+            s = fma(dop::kTab.b[10], K[10][i], s);
+            s = fma(dop::kTab.b[11], K[11][i], s);
+            s = fma(dop::kTab.b[12], K[12][i], s);
+            kb[i] = s;
+            y5[i] = fma(h, s, y[i]);
+            const double sk = fma(rtol, fmax(fabs(y[i]), fabs(y5[i])), atol);
+            double e3 = fma(-dop::kTab.bhh[0], K[1][i], s);
+            e3 = fma(-dop::kTab.bhh[1], K[9][i], e3);
+            e3 = fma(-dop::kTab.bhh[2], K[12][i], e3);
+            e3 /= sk;
+            err2 = fma(e3, e3, err2);
+            double e5 = dop::kTab.er[1] * K[1][i];
+            e5 = fma(dop::kTab.er[6], K[6][i], e5);
+            e5 = fma(dop::kTab.er[7], K[7][i], e5);
+            e5 = fma(dop::kTab.er[8], K[8][i], e5);
+            e5 = fma(dop::kTab.er[9], K[9][i], e5);
+            e5 = fma(dop::kTab.er[10], K[10][i], e5);
+            e5 = fma(dop::kTab.er[11], K[11][i], e5);
+            e5 = fma(dop::kTab.er[12], K[12][i], e5);
+            e5 /= sk;
+            err = fma(e5, e5, err);
+        }
+        double deno = fma(0.01, err2, err);
+        if (deno <= 0.0) deno = 1.0;
+        err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
+        const double fac11 = detail::pow_eighth(err);
+        const double fac = fmax(kFacc2, fmin(kFacc1, fac11 / kSafe));  // beta = 0
+        double hnew = h / fac;
+        if (err <= 1.0) {
+            // ---- accepted
+            facold = fmax(err, 1.0e-4);
+            ++cnt.accepted;
+            rhs(xph, y5, K[13]);  // first-same-as-last slope
+            if (DENSE) {
+                if (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0) {
+                    ++cnt.dense;
+                    double rc[8][N];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        rc[0][i] = y[i];
+                        const double ydiff = y5[i] - y[i];
+                        rc[1][i] = ydiff;
+                        const double bspl = fma(h, K[1][i], -ydiff);
+                        rc[2][i] = bspl;
+                        rc[3][i] = ydiff - h * K[13][i] - bspl;
+                    }
+                    detail::do_stage<14>(rhs, x, h, y, K);
+                    detail::do_stage<15>(rhs, x, h, y, K);
+                    detail::do_stage<16>(rhs, x, h, y, K);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        rc[4][i] = h * detail::dense_row<4, N>(K, i, std::make_integer_sequence<int, 16>{});
+                        rc[5][i] = h * detail::dense_row<5, N>(K, i, std::make_integer_sequence<int, 16>{});
+                        rc[6][i] = h * detail::dense_row<6, N>(K, i, std::make_integer_sequence<int, 16>{});
+                        rc[7][i] = h * detail::dense_row<7, N>(K, i, std::make_integer_sequence<int, 16>{});
+                    }
+                    do {
+                        const double th = (tnext - x) / h, th1 = 1.0 - th;
+                        double yo[N];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            double v = th * rc[7][i];
+                            v = th1 * (rc[6][i] + v);
+                            v = th * (rc[5][i] + v);
+                            v = th1 * (rc[4][i] + v);
+                            v = th * (rc[3][i] + v);
+                            v = th1 * (rc[2][i] + v);
+                            v = th * (rc[1][i] + v);
+                            yo[i] = rc[0][i] + v;
+                        }
+                        sink(iout, yo);
+                        ++iout;
+                        tnext = t_out(iout);
+                    } while (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                K[1][i] = K[13][i];
+                y[i] = y5[i];
+            }
+            x = xph;
+            if (last) break;
+            if (fabs(hnew) > hmax) hnew = posneg * hmax;
+            if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
+            reject = false;
+        } else {
+            // ---- rejected
+            hnew = h / fmin(kFacc1, fac11 / kSafe);
+            reject = true;
+            last = false;
+            ++cnt.rejected;
+        }
+        h = hnew;
+    }
+    if (DENSE && status == B200CS_ST_OK && n_out >= 2) sink(n_out - 1, y);
+    (void)facold;
+    return status;
+}
+
+}  // namespace b200cs

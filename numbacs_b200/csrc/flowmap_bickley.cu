@@ -1,0 +1,8 @@
+// flowmap_bickley.cu -- instantiates the flow-map kernels for one flow kind (see flowmap_kernel.cuh).
+#include "flowmap_kernel.cuh"
+
+namespace b200cs {
+
+void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s) { launch_rhs<BickleyJet>(A, grid_mode, s); }
+
+}  // namespace b200cs

@@ -1,0 +1,68 @@
+// flowmap_dispatch.cu -- flow-kind dispatch of the flow-map kernels + the RHS evaluation kernel.
+#include "common.cuh"
+#include "flows.cuh"
+#include "launch.cuh"
+
+namespace b200cs {
+
+void launch_flowmap_dg(const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_flowmap_abc(const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cudaStream_t s);
+
+void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s) {
+    switch (f.kind) {
+    case B200CS_FLOW_DOUBLE_GYRE: launch_flowmap_dg(A, grid_mode, s); break;
+    case B200CS_FLOW_BICKLEY_JET: launch_flowmap_bickley(A, grid_mode, s); break;
+    case B200CS_FLOW_ABC:
+        launch_flowmap_abc(A, grid_mode, s);
+        break;
+    case B200CS_FLOW_SPLINE2D:
+        launch_flowmap_spline(f.spherical, A, grid_mode, s);
+        break;
+    default:
+        set_error("handle is not a flow (kind %d)", f.kind);
+        throw Fail{B200CS_E_HANDLE};
+    }
+}
+
+// ---------------------------------------------------------------- RHS evaluation (diagnostic)
+namespace {
+template <class Rhs>
+__global__ void rhs_kernel(const __grid_constant__ RhsParams P, const double *__restrict__ t,
+                           const double *__restrict__ y, long long npts, double *__restrict__ dy) {
+    constexpr int N = Rhs::N;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    const Rhs rhs(P);
+    double yy[N], d[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) yy[i] = y[q * N + i];
+    rhs(t[q], yy, d);
+#pragma unroll
+    for (int i = 0; i < N; ++i) dy[q * N + i] = d[i];
+}
+}  // namespace
+
+void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, const double *y,
+                     long long npts, double *dy, cudaStream_t s) {
+    const int b = 128;
+    const unsigned g = (unsigned)((npts + b - 1) / b);
+    if (!g) return;
+    switch (f.kind) {
+    case B200CS_FLOW_DOUBLE_GYRE: rhs_kernel<DoubleGyre><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
+    case B200CS_FLOW_BICKLEY_JET: rhs_kernel<BickleyJet><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
+    case B200CS_FLOW_ABC: rhs_kernel<Abc><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
+    case B200CS_FLOW_SPLINE2D:
+        if (f.spherical == 1) rhs_kernel<Spline2D<1>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        else if (f.spherical == 2) rhs_kernel<Spline2D<2>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        else rhs_kernel<Spline2D<0>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        break;
+    default:
+        set_error("handle is not a flow (kind %d)", f.kind);
+        throw Fail{B200CS_E_HANDLE};
+    }
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+}  // namespace b200cs

@@ -1,0 +1,12 @@
+// flowmap_spline.cu -- instantiates the flow-map kernels for one flow kind (see flowmap_kernel.cuh).
+#include "flowmap_kernel.cuh"
+
+namespace b200cs {
+
+void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cudaStream_t s) {
+    if (spherical == 1) launch_rhs<Spline2D<1>>(A, grid_mode, s);
+    else if (spherical == 2) launch_rhs<Spline2D<2>>(A, grid_mode, s);
+    else launch_rhs<Spline2D<0>>(A, grid_mode, s);
+}
+
+}  // namespace b200cs

@@ -1,0 +1,116 @@
+// flows.cuh -- device right-hand sides: the GPU-side flow registry behind `funcptr`.
+//
+// Each functor is the device implementation of one numba @cfunc(lsoda_sig) the reference builds
+// (signature rhs(t, y, dy, p), /root/reference/src/numbacs/flows.py):
+//   DoubleGyre  flows.py:1146-1158      BickleyJet  flows.py:1182-1213
+//   Abc         flows.py:1249-1258      Spline2D    flows.py:156-253 (spherical 0 / 1 / 2)
+// Conventions kept from the reference: tt = p[0]*t, dy = p[0]*v(tt, y) (userguide.rst:217-227);
+// `params` is used verbatim; operation order follows the reference expressions (FMA contraction
+// is allowed, it perturbs results at the 1-ulp level only).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fastmath.cuh"
+#include "spline.cuh"
+
+namespace b200cs {
+
+constexpr int kMaxParams = 16;
+constexpr double kPi = 3.141592653589793;
+
+struct RhsParams {
+    double p[kMaxParams];
+    SplineGridDev grid;       // Spline2D only
+    const double2 *coef_uv;   // Spline2D only
+    double r;                 // Spline2D spherical radius
+};
+
+struct DoubleGyre {
+    static constexpr int N = 2;
+    double p0, eps, omega, psi, alpha, piA, npiA;
+    __device__ __forceinline__ explicit DoubleGyre(const RhsParams &P)
+        : p0(P.p[0]), eps(P.p[2]), omega(P.p[4]), psi(P.p[5]), alpha(P.p[3]),
+          piA(kPi * P.p[1]), npiA(-kPi * P.p[1]) {}
+    __device__ __forceinline__ void operator()(double t, const double (&y)[2], double (&dy)[2]) const {
+        const double tt = p0 * t;
+        const double a = eps * sin_fast(fma(omega, tt, psi));
+        const double b = 1.0 - 2.0 * a;
+        const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
+        const double df = fma(2.0 * a, y[0], b);
+        double sf, cf, sy, cy;
+        sincos_fast(kPi * f, &sf, &cf);
+        sincos_fast(kPi * y[1], &sy, &cy);
+        dy[0] = p0 * fma(npiA * sf, cy, -(alpha * y[0]));
+        dy[1] = p0 * fma(piA * cf * sy, df, -(alpha * y[1]));
+    }
+};
+
+struct BickleyJet {
+    static constexpr int N = 2;
+    const double *p;
+    __device__ __forceinline__ explicit BickleyJet(const RhsParams &P) : p(P.p) {}
+    __device__ __forceinline__ void operator()(double t, const double (&y)[2], double (&dy)[2]) const {
+        const double tt = p[0] * t;
+        const double Y = y[1] / p[2];
+        const double ch = cosh(Y);
+        const double sech2 = 1.0 / (ch * ch);
+        double s1, c1, s2, c2, s3, c3;
+        sincos_fast(p[6] * (y[0] - p[9] * tt), &s1, &c1);
+        sincos_fast(p[7] * (y[0] - p[10] * tt), &s2, &c2);
+        sincos_fast(p[8] * (y[0] - p[11] * tt), &s3, &c3);
+        const double csum = fma(p[5], c3, fma(p[4], c2, p[3] * c1));
+        const double ssum = fma(p[5] * p[8], s3, fma(p[4] * p[7], s2, p[3] * p[6] * s1));
+        dy[0] = p[0] * fma(2.0 * p[1] * tanh(Y) * sech2, csum, p[1] * sech2);
+        dy[1] = -p[0] * (p[1] * p[2] * sech2 * ssum);
+    }
+};
+
+struct Abc {
+    static constexpr int N = 3;
+    const double *p;
+    __device__ __forceinline__ explicit Abc(const RhsParams &P) : p(P.p) {}
+    __device__ __forceinline__ void operator()(double t, const double (&y)[3], double (&dy)[3]) const {
+        const double tt = p[0] * t;
+        const double At = fma(p[4] * tt, sin_fast(kPi * tt), p[1]);
+        double s1, c1;
+        sincos_fast(y[1], &s1, &c1);
+        dy[0] = p[0] * fma(At, sin_fast(y[2]), p[3] * c1);
+        dy[1] = p[0] * fma(p[2], sin_fast(y[0]), At * c1);
+        // the reference uses y[1] in both terms of dz (flows.py:1258); kept for parity
+        dy[2] = p[0] * fma(p[3], s1, p[2] * c1);
+    }
+};
+
+// Python float modulo: the result takes the sign of the (positive) divisor
+__device__ __forceinline__ double pymod_pos(double a, double m) {
+    double r = fmod(a, m);
+    if (r < 0.0) r += m;
+    return r;
+}
+
+template <int SPHERICAL>
+struct Spline2D {
+    static constexpr int N = 2;
+    const RhsParams &P;
+    __device__ __forceinline__ explicit Spline2D(const RhsParams &P_) : P(P_) {}
+    __device__ __forceinline__ void operator()(double t, const double (&y)[2], double (&dy)[2]) const {
+        const double p0 = P.p[0];
+        const double tt = p0 * t;
+        double xx = y[0];
+        const double yy = y[1];
+        if (SPHERICAL == 1) xx = pymod_pos(y[0] - 180.0, 360.0) - 180.0;
+        if (SPHERICAL == 2) xx = pymod_pos(y[0], 360.0);
+        double u, v;
+        eval_spline_uv(P.grid, P.coef_uv, tt, xx, yy, u, v);
+        if (SPHERICAL) {
+            // ((p0*u)*180) / (pi*r*cos(yy*pi/180))   (flows.py:165-196)
+            dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos_fast(yy * kPi / 180.0));
+            dy[1] = ((p0 * v) * 180.0) / (kPi * P.r);
+        } else {
+            dy[0] = p0 * u;
+            dy[1] = p0 * v;
+        }
+    }
+};
+
+}  // namespace b200cs

@@ -1,0 +1,54 @@
+// launch.cuh -- host-side launch interfaces between capi.cu and the kernel translation units.
+#pragma once
+#include "common.cuh"
+#include "flows.cuh"
+
+namespace b200cs {
+
+// Arguments of the flow-map kernels (passed as one __grid_constant__ struct: every field is
+// warp-uniform and lands in the constant bank).
+struct IntegArgs {
+    RhsParams rhs;
+    double x0, xend;  // solver times: params[0]*t0, params[0]*(t0+T)   (integration.py:164)
+    double rtol, atol;
+    // output times t_k = out_p0 * (out_t0 + k*out_step), k < n_out   (n_out == 0: final state only)
+    double out_p0, out_t0, out_step;
+    int n_out;
+    int out_aligned16;
+    // particles: 'ij' grid (x[nx], y[ny]) or a point list pts[npts, N]
+    const double *x, *y;
+    long long nx, ny;
+    const double *pts;
+    long long npts;
+    const uint8_t *mask;
+    double *out;
+    int *status;
+    int *steps;
+    unsigned long long *stats;
+};
+
+void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, const double *y,
+                     long long npts, double *dy, cudaStream_t s);
+
+// FTLE of rows [row_lo, row_hi) of a flow-map slab fm[nx, ny, 2]; out row r - row_lo.
+// `lo_is_border` / `hi_is_border`: slab row 0 / nx-1 is a true domain border (ftle = 0).
+void launch_ftle(const double *fm, long long nx, long long ny, double T, double dx, double dy,
+                 const uint8_t *mask, double *out, long long row_lo, long long row_hi,
+                 bool lo_is_border, bool hi_is_border, cudaStream_t s);
+
+SplineGridDev make_grid_dev(const FlowSpec &f);
+
+void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s);
+void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
+                      const double *yr, long long nrav, double *sums, cudaStream_t s);
+void launch_lavd(const FlowSpec &f, const double *fm_n, long long npts, long long n, const double *tspan,
+                 const double *vavg, double period_x, double period_y, const uint8_t *mask, double *lavd,
+                 cudaStream_t s);
+void launch_prefilter3(const double *data, long long n0, long long n1, long long n2, double *coefs,
+                       cudaStream_t s);
+void launch_div_scalar(double *a, long long n, double d, cudaStream_t s);
+void launch_interleave(const double *u, const double *v, long long count, double2 *uv, cudaStream_t s);
+void run_fp64_peak(int iters, double *tflops, double *ms);
+
+}  // namespace b200cs

@@ -1,0 +1,166 @@
+// spline.cuh -- device evaluators over get_interp_arrays_2D / get_interp_arrays_scalar outputs.
+//
+// Replaces interpolation.splines.eval_spline(grid, C, point, k=3, extrap_mode) as called at
+// /root/reference/src/numbacs/flows.py:168-253 (velocity, inside the RHS) and flows.py:409
+// (scalar vorticity), and eval_linear at flows.py:631 (trilinear scalar).
+//
+// Layout: coefficients of the two velocity components are interleaved as double2 (u, v) so one
+// 16-byte load serves both and the blending weights are computed once per RHS (the reference
+// evaluates u and v separately and recomputes them).  C-order (t, x, y), y fastest: the four
+// y-taps of one (t, x) pair are one contiguous 64-byte run.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b200cs {
+
+struct SplineGridDev {
+    double a[3];      // axis start
+    double b[3];      // axis end
+    double delta[3];  // (b - a) / (n - 1)
+    double inv_delta[3];
+    int n[3];         // data points per axis
+    long long s0, s1; // element strides of axes 0 and 1 of the coefficient array
+    int extrap;       // B200CS_EXTRAP_*
+};
+
+// cell index and local coordinate:  i = clamp(floor((x-a)/delta), 0, n-2),  lam = ((x-a) - i*delta)/delta
+// (the product i*delta is rounded before the subtraction, as in unfused CPU arithmetic)
+__device__ __forceinline__ void axis_locate(const SplineGridDev &g, int d, double x, int &i, double &lam) {
+    const double dd = x - g.a[d];
+    double fi = floor(dd * g.inv_delta[d]);
+    fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
+    i = (int)fi;
+    const double r = __dsub_rn(dd, __dmul_rn(fi, g.delta[d]));
+    lam = r * g.inv_delta[d];
+}
+
+// uniform cubic B-spline blending weights; outside [0,1] they continue linearly when the
+// extrapolation mode is 'linear'.
+__device__ __forceinline__ void bspline_weights(double l, bool linear_ext, double (&P)[4]) {
+    const double s = 1.0 / 6.0;
+    if (linear_ext && l < 0.0) {
+        P[0] = fma(-0.5, l, s);
+        P[1] = 4.0 * s;
+        P[2] = fma(0.5, l, s);
+        P[3] = 0.0;
+    } else if (linear_ext && l > 1.0) {
+        const double m = l - 1.0;
+        P[0] = 0.0;
+        P[1] = fma(-0.5, m, s);
+        P[2] = 4.0 * s;
+        P[3] = fma(0.5, m, s);
+    } else {
+        const double l2 = l * l, l3 = l2 * l;
+        P[0] = fma(-s, l3, fma(0.5, l2, fma(-0.5, l, s)));
+        P[1] = fma(0.5, l3, fma(-1.0, l2, 4.0 * s));
+        P[2] = fma(-0.5, l3, fma(0.5, l2, fma(0.5, l, s)));
+        P[3] = s * l3;
+    }
+}
+
+// Applies the extrapolation rule to one coordinate. Returns false when the point is outside the
+// grid and the mode is 'constant' (value 0).
+__device__ __forceinline__ bool extrap_coord(const SplineGridDev &g, int d, double &x) {
+    if (g.extrap == B200CS_EXTRAP_CONSTANT) {
+        if (x < g.a[d] || x > g.b[d]) return false;
+    } else if (g.extrap == B200CS_EXTRAP_NEAREST) {
+        x = fmax(g.a[d], fmin(g.b[d], x));
+    }
+    return true;
+}
+
+// 64-tap tri-cubic evaluation of an interleaved (u, v) field.
+__device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const double2 *__restrict__ C,
+                                               double t, double x, double y, double &u, double &v) {
+    u = 0.0;
+    v = 0.0;
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return;
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
+    double P0[4], P1[4], P2[4];
+    bspline_weights(l0, lin, P0);
+    bspline_weights(l1, lin, P1);
+    bspline_weights(l2, lin, P2);
+    const double2 *base = C + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
+    double au = 0.0, av = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double bu = 0.0, bv = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double2 *c = base + a * g.s0 + b * g.s1;
+            const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
+            const double cu = fma(P2[3], c3.x, fma(P2[2], c2.x, fma(P2[1], c1.x, P2[0] * c0.x)));
+            const double cv = fma(P2[3], c3.y, fma(P2[2], c2.y, fma(P2[1], c1.y, P2[0] * c0.y)));
+            bu = fma(P1[b], cu, bu);
+            bv = fma(P1[b], cv, bv);
+        }
+        au = fma(P0[a], bu, au);
+        av = fma(P0[a], bv, av);
+    }
+    u = au;
+    v = av;
+}
+
+// scalar tri-cubic
+__device__ __forceinline__ double eval_spline_s(const SplineGridDev &g, const double *__restrict__ C,
+                                                double t, double x, double y) {
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return 0.0;
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
+    double P0[4], P1[4], P2[4];
+    bspline_weights(l0, lin, P0);
+    bspline_weights(l1, lin, P1);
+    bspline_weights(l2, lin, P2);
+    const double *base = C + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
+    double acc0 = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        double acc1 = 0.0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double *c = base + a * g.s0 + b * g.s1;
+            const double acc2 =
+                fma(P2[3], __ldg(c + 3), fma(P2[2], __ldg(c + 2), fma(P2[1], __ldg(c + 1), P2[0] * __ldg(c))));
+            acc1 = fma(P1[b], acc2, acc1);
+        }
+        acc0 = fma(P0[a], acc1, acc0);
+    }
+    return acc0;
+}
+
+// scalar trilinear on the raw (n0, n1, n2) data
+__device__ __forceinline__ double eval_linear_s(const SplineGridDev &g, const double *__restrict__ F,
+                                                double t, double x, double y) {
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return 0.0;
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const double *c = F + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double wa = a ? l0 : 1.0 - l0;
+        double va = 0.0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double wb = b ? l1 : 1.0 - l1;
+            const double *cc = c + a * g.s0 + b * g.s1;
+            va = fma(wb, fma(l2, __ldg(cc + 1), (1.0 - l2) * __ldg(cc)), va);
+        }
+        v = fma(wa, va, v);
+    }
+    return v;
+}
+
+}  // namespace b200cs

@@ -1,0 +1,95 @@
+"""Diagnostics -- drop-in for the hot-path part of ``numbacs.diagnostics``.
+
+ftle_grid_2D (diagnostics.py:21-65) and lavd_grid_2D (272-379) of the reference with the same
+arguments and layouts; both accept numpy arrays or torch CUDA tensors (then nothing crosses PCIe)
+and run as CUDA kernels of libb200cs.so.  flowmap_ftle_grid_2D is the fused convenience call for
+the README workflow (flow map + FTLE with the flow map kept on the device).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .flows import ScalarField
+from .integration import _info_bufs, _fill_info, _method
+
+__all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D"]
+
+
+def ftle_grid_2D(flowmap, T, dx, dy, mask=None, *, device_out=False):
+    """FTLE field (nx, ny) from a flow map (nx, ny, 2) for integration time T."""
+    fm, ma = _lib.arg_in(flowmap), _lib.mask_in(mask)
+    if fm.obj.ndim != 3 or fm.obj.shape[2] != 2:
+        raise ValueError("flowmap must have shape (nx, ny, 2)")
+    nx, ny = int(fm.obj.shape[0]), int(fm.obj.shape[1])
+    dev = bool(device_out or fm.on_device)
+    out = _lib.alloc_out((nx, ny), np.float64, dev)
+    _lib.check(_lib.load().b200cs_ftle_grid_2d(fm.ptr, nx, ny, float(T), float(dx), float(dy),
+                                               ma.ptr, out.ptr, _lib.current_stream(dev)))
+    return out.obj
+
+
+def ftle_slab_2D(flowmap, T, dx, dy, halo=(0, 0), mask=None, *, device_out=False):
+    """FTLE of a row slab (nx, ny, 2) that carries halo[0] / halo[1] stencil-only rows at its
+    first / last row (multi-GPU row blocks) -> (nx - halo[0] - halo[1], ny)."""
+    fm, ma = _lib.arg_in(flowmap), _lib.mask_in(mask)
+    nx, ny = int(fm.obj.shape[0]), int(fm.obj.shape[1])
+    dev = bool(device_out or fm.on_device)
+    out = _lib.alloc_out((nx - halo[0] - halo[1], ny), np.float64, dev)
+    _lib.check(_lib.load().b200cs_ftle_slab_2d(fm.ptr, nx, ny, float(T), float(dx), float(dy), ma.ptr,
+                                               int(halo[0]), int(halo[1]), out.ptr,
+                                               _lib.current_stream(dev)))
+    return out.obj
+
+
+def flowmap_ftle_grid_2D(funcptr, t0, T, x, y, params, dx, dy, method="dop853", rtol=1e-6,
+                         atol=1e-8, mask=None, *, return_flowmap=True, device_out=False,
+                         info=None, halo=(0, 0)):
+    """flowmap_grid_2D + ftle_grid_2D in one call.  Returns (flowmap or None, ftle).
+
+    halo=(lo, hi): the first / last row of x is a stencil-only halo row (multi-GPU row blocks):
+    it is integrated but its FTLE row is not produced."""
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
+    nx, ny = int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    dev = bool(device_out or xa.on_device or ya.on_device)
+    fm = _lib.alloc_out((nx, ny, 2), np.float64, dev) if return_flowmap else _lib.Arg(None, None, False)
+    ftle = _lib.alloc_out((nx - halo[0] - halo[1], ny), np.float64, dev)
+    status, _, stats = _info_bufs(info, (nx, ny), dev)
+    _lib.check(_lib.load().b200cs_flowmap_ftle_grid_2d(
+        int(funcptr), float(t0), float(T), xa.ptr, nx, ya.ptr, ny, pa.ptr, int(pa.obj.shape[0]),
+        _method(method), float(rtol), float(atol), ma.ptr, float(dx), float(dy), int(halo[0]),
+        int(halo[1]), fm.ptr, ftle.ptr, status.ptr, stats.ptr, _lib.current_stream(dev)))
+    if info is not None:
+        info["status"], info["stats"] = status.obj, stats.obj
+    return fm.obj, ftle.obj
+
+
+def lavd_grid_2D(flowmap_n, tspan, T, vort_interp, xrav, yrav, period_x=0.0, period_y=0.0,
+                 mask=None, *, device_out=False, vort_avg=None):
+    """LAVD field (nx, ny) from trajectories flowmap_n (nx, ny, n, 2) at times tspan[n].
+
+    `vort_interp` must be a ScalarField from numbacs_b200.flows.get_callable_scalar(_linear).
+    `T` is unused, as in the reference.  `vort_avg` (optional, [n]) supplies precomputed spatial
+    means (used by the sharded multi-GPU driver)."""
+    if not isinstance(vort_interp, ScalarField):
+        raise NotImplementedError(
+            "vort_interp must come from numbacs_b200.flows.get_callable_scalar / "
+            "get_callable_scalar_linear: an arbitrary jit-callable cannot run on the GPU")
+    fm, ts, ma = _lib.arg_in(flowmap_n), _lib.arg_in(tspan), _lib.mask_in(mask)
+    if fm.obj.ndim != 4 or fm.obj.shape[3] != 2:
+        raise ValueError("flowmap_n must have shape (nx, ny, n, 2)")
+    nx, ny, n = (int(v) for v in fm.obj.shape[:3])
+    xr, yr = _lib.arg_in(xrav), _lib.arg_in(yrav)
+    nrav = int(xr.obj.shape[0])
+    dev = bool(device_out or fm.on_device)
+    out = _lib.alloc_out((nx, ny), np.float64, dev)
+    if vort_avg is not None:
+        va = _lib.arg_in(vort_avg)
+        va_ptr, va_in = va.ptr, 1
+    else:
+        va = None
+        va_ptr, va_in = None, 0
+    _lib.check(_lib.load().b200cs_lavd_grid_2d(
+        fm.ptr, nx, ny, n, ts.ptr, vort_interp.handle, xr.ptr, yr.ptr, nrav, float(period_x),
+        float(period_y), ma.ptr, va_ptr, va_in, out.ptr, _lib.current_stream(dev)))
+    return out.obj

@@ -1,0 +1,110 @@
+"""Particle integration -- drop-in for the hot-path part of ``numbacs.integration``.
+
+flowmap (integration.py:7), flowmap_n (64), flowmap_grid_2D (123), flowmap_n_grid_2D (467) of the
+reference, same positional arguments, defaults (method="dop853", rtol=1e-6, atol=1e-8, mask=None)
+and output layouts ('ij' indexing, float64, zeros where masked).  The work is done by the
+one-thread-per-particle DOP853 kernels of libb200cs.so; ``funcptr`` must be a handle from
+``numbacs_b200.flows``.
+
+Extras (keyword-only, not in the reference):
+  device_out : return torch CUDA tensors instead of numpy arrays (no PCIe round trip before
+               ftle_grid_2D / lavd_grid_2D, which accept them).  Implied when an input is a
+               CUDA tensor.
+  info       : a dict that receives 'status' (per-particle numbalsoda `success`, which the
+               reference silently drops), 'steps' (accepted, rejected attempts per particle) and
+               'stats' = [sum nfev, sum accepted, sum rejected].
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D"]
+
+
+def _method(method):
+    m = method.lower()
+    if m == "dop853":
+        return _lib.METHOD_DOP853
+    if m == "lsoda":
+        raise NotImplementedError("method='lsoda' is not implemented on the GPU; use 'dop853'")
+    raise ValueError(f"unknown method {method!r}")
+
+
+def _info_bufs(info, shape, device):
+    if info is None:
+        return _lib.Arg(None, None, False), _lib.Arg(None, None, False), _lib.Arg(None, None, False)
+    status = _lib.alloc_out(shape, np.int32, device)
+    steps = _lib.alloc_out(shape + (2,), np.int32, device)
+    if device:
+        import torch
+        st = torch.zeros(3, dtype=torch.int64, device="cuda")
+        stats = _lib.Arg(st, C.c_void_p(st.data_ptr()), True)
+    else:
+        st = np.zeros(3, np.int64)
+        stats = _lib.Arg(st, C.c_void_p(st.ctypes.data), False)
+    return status, steps, stats
+
+
+def _fill_info(info, status, steps, stats):
+    if info is not None:
+        info["status"], info["steps"], info["stats"] = status.obj, steps.obj, stats.obj
+
+
+def _grid(funcptr, t0, T, x, y, params, n, method, rtol, atol, mask, device_out, info):
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
+    nx, ny = int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    if ma.obj is not None and tuple(ma.obj.shape) != (nx, ny):
+        raise ValueError(f"mask must have shape {(nx, ny)}")
+    dev = bool(device_out or xa.on_device or ya.on_device or ma.on_device)
+    out = _lib.alloc_out((nx, ny, 2) if n == 0 else (nx, ny, n, 2), np.float64, dev)
+    tspan = np.empty(max(n, 1), np.float64)
+    status, steps, stats = _info_bufs(info, (nx, ny), dev)
+    _lib.check(_lib.load().b200cs_flowmap_grid_2d(
+        int(funcptr), float(t0), float(T), xa.ptr, nx, ya.ptr, ny, pa.ptr, int(pa.obj.shape[0]),
+        _method(method), float(rtol), float(atol), ma.ptr, int(n), out.ptr,
+        C.c_void_p(tspan.ctypes.data), status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
+    _fill_info(info, status, steps, stats)
+    return out.obj, tspan
+
+
+def _pts(funcptr, t0, T, pts, params, n, method, rtol, atol, mask, device_out, info):
+    qa, pa, ma = _lib.arg_in(pts), _lib.arg_in(params), _lib.mask_in(mask)
+    if qa.obj.ndim != 2:
+        raise ValueError("pts must have shape (npts, N)")
+    npts, nd = int(qa.obj.shape[0]), int(qa.obj.shape[1])
+    dev = bool(device_out or qa.on_device or ma.on_device)
+    out = _lib.alloc_out((npts, nd) if n == 0 else (npts, n, nd), np.float64, dev)
+    tspan = np.empty(max(n, 1), np.float64)
+    status, steps, stats = _info_bufs(info, (npts,), dev)
+    _lib.check(_lib.load().b200cs_flowmap_pts(
+        int(funcptr), float(t0), float(T), qa.ptr, npts, nd, pa.ptr, int(pa.obj.shape[0]),
+        _method(method), float(rtol), float(atol), ma.ptr, int(n), out.ptr,
+        C.c_void_p(tspan.ctypes.data), status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
+    _fill_info(info, status, steps, stats)
+    return out.obj, tspan
+
+
+def flowmap(funcptr, t0, T, pts, params, method="dop853", rtol=1e-6, atol=1e-8, mask=None, *,
+            device_out=False, info=None):
+    """Final positions of the particles pts[npts, N] after [t0, t0+T] -> (npts, N)."""
+    return _pts(funcptr, t0, T, pts, params, 0, method, rtol, atol, mask, device_out, info)[0]
+
+
+def flowmap_n(funcptr, t0, T, pts, params, method="dop853", n=2, rtol=1e-6, atol=1e-8, mask=None,
+              *, device_out=False, info=None):
+    """Positions at n equally spaced times -> ((npts, n, N), t_eval[n])."""
+    return _pts(funcptr, t0, T, pts, params, n, method, rtol, atol, mask, device_out, info)
+
+
+def flowmap_grid_2D(funcptr, t0, T, x, y, params, method="dop853", rtol=1e-6, atol=1e-8,
+                    mask=None, *, device_out=False, info=None):
+    """Flow map at the final time over the 'ij' grid (x, y) -> (nx, ny, 2)."""
+    return _grid(funcptr, t0, T, x, y, params, 0, method, rtol, atol, mask, device_out, info)[0]
+
+
+def flowmap_n_grid_2D(funcptr, t0, T, x, y, params, n=50, method="dop853", rtol=1e-6, atol=1e-8,
+                      mask=None, *, device_out=False, info=None):
+    """Flow map at n equally spaced times over the grid -> ((nx, ny, n, 2), t_eval[n])."""
+    return _grid(funcptr, t0, T, x, y, params, n, method, rtol, atol, mask, device_out, info)

@@ -1,0 +1,499 @@
+"""GPU parity tests: the CUDA path (through the ctypes C-ABI of libb200cs.so) against the CPU oracle
+and the frozen reference goldens.
+
+Tolerances (north_star): flow-map positions max|dx| <= 1e-8 x domain size under identical rtol/atol;
+FTLE relative L2 <= 1e-6.  The position gate is evaluated over particles whose (accepted,
+rejected) step counts equal the oracle's -- DOP853's accept/reject decisions are discontinuous, so
+a particle whose decision flips differs at the solver's truncation level (~1e-5) no matter how
+close the arithmetic is -- and the number of such particles is gated separately.
+
+For strongly stretching cases (Bickley jet T = 6, spline fields) even a ONE-ULP change of one
+parameter moves some trajectories of the CPU oracle itself by far more than 1e-8 x L (measured:
+1.4e-5 at Bickley T = 6), because a noisy error estimate (err << 1) feeds the step-size formula.
+There the gate is calibrated in-test: the GPU may differ from the oracle by no more than a small
+multiple of what the oracle differs from itself under a 1-ulp parameter perturbation, and the
+bulk statistics (median, 99th percentile) must still meet 1e-8 x L.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def apply_mask(arr, mask):
+    out = arr.copy()
+    out[mask] = 0.0
+    return out
+
+
+@pytest.fixture(scope="module")
+def nb(lib):
+    import numbacs_b200 as nb
+    from numbacs_b200 import _lib
+    assert _lib.device_count() >= 1
+    return nb
+
+
+def ftle_rel_l2(ft, fto, same=None):
+    """Relative L2 error of an FTLE field; with `same` (per-particle step-count equality) the
+    pixels whose 5-point stencil touches a step-count-mismatched particle are left out."""
+    keep = np.ones(ft.shape, bool)
+    if same is not None:
+        bad = ~same
+        touch = bad.copy()
+        touch[1:] |= bad[:-1]
+        touch[:-1] |= bad[1:]
+        touch[:, 1:] |= bad[:, :-1]
+        touch[:, :-1] |= bad[:, 1:]
+        keep = ~touch
+    return float(np.linalg.norm((ft - fto)[keep]) / np.linalg.norm(fto[keep]))
+
+
+def compare_flowmaps(gpu, info, ora, steps_o, L):
+    """-> dict with mismatch count and error statistics relative to the domain size L."""
+    d = (np.abs(gpu - ora) / np.asarray(L)).max(axis=-1)
+    same = (np.asarray(info["steps"]) == steps_o).all(axis=-1)
+    return {"n": d.size, "mismatch": int((~same).sum()),
+            "max_match": float(d[same].max()) if same.any() else 0.0,
+            "max_all": float(d.max()), "p99": float(np.percentile(d, 99)),
+            "median": float(np.median(d))}
+
+
+# ------------------------------------------------------------------ reference goldens (float32)
+
+def test_flowmap_grid_2D_golden(nb, golden, coords_dg, mask_dg):
+    """tests/test_integration.py:55-64 of the reference, on the GPU."""
+    x, y = coords_dg
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, x, y, p)
+    assert fm.shape == (21, 11, 2) and fm.dtype == np.float64
+    assert np.array_equal(fm.astype(np.float32), golden["ref_fm"])
+    fm_m = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, x, y, p, mask=mask_dg)
+    assert np.array_equal(fm_m.astype(np.float32), apply_mask(golden["ref_fm"], mask_dg))
+    assert np.array_equal(fm_m[~mask_dg], fm[~mask_dg])
+
+
+def test_flowmap_and_flowmap_n_golden(nb, golden, coords_dg):
+    """tests/test_integration.py:38-52."""
+    x, y = coords_dg
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    pts = np.column_stack((X.ravel(), Y.ravel()))
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fm = nb.integration.flowmap(f, 0.0, 8.0, pts, p).reshape(21, 11, 2)
+    assert np.array_equal(fm.astype(np.float32), golden["ref_fm"])
+    fmn, t_eval = nb.integration.flowmap_n(f, 0.0, 8.0, pts, p, n=4)
+    assert np.allclose(t_eval, p[0] * np.linspace(0.0, 8.0, 4))
+    assert np.array_equal(fmn.reshape(21, 11, 4, 2).astype(np.float32), golden["ref_fm_n"])
+
+
+def test_flowmap_n_grid_2D_golden(nb, golden, coords_dg, mask_dg):
+    """tests/test_integration.py:78-89."""
+    x, y = coords_dg
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fmn, t_eval = nb.integration.flowmap_n_grid_2D(f, 0.0, 8.0, x, y, p, n=4)
+    assert fmn.shape == (21, 11, 4, 2)
+    assert np.allclose(t_eval, p[0] * np.linspace(0.0, 8.0, 4))
+    assert np.array_equal(fmn.astype(np.float32), golden["ref_fm_n"])
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, x, y, p)
+    assert np.array_equal(fmn[:, :, -1, :], fm)          # one continuous integration
+    assert np.array_equal(fmn[:, :, 0, 0], np.broadcast_to(x[:, None], (21, 11)))
+    fmn_m, _ = nb.integration.flowmap_n_grid_2D(f, 0.0, 8.0, x, y, p, n=4, mask=mask_dg)
+    assert np.array_equal(fmn_m.astype(np.float32), apply_mask(golden["ref_fm_n"], mask_dg))
+
+
+def test_ftle_golden(nb, golden, coords_dg, mask_dg):
+    """tests/test_diagnostics.py:82-96."""
+    x, y = coords_dg
+    ftle = nb.diagnostics.ftle_grid_2D(golden["ref_fm"], 8.0, x[1], y[1])
+    assert np.allclose(ftle.astype(np.float32), golden["ref_ftle"])
+    ftle_m = nb.diagnostics.ftle_grid_2D(golden["ref_fm"], 8.0, x[1], y[1], mask=mask_dg)
+    assert np.allclose(ftle_m.astype(np.float32), apply_mask(golden["ref_ftle"], mask_dg))
+
+
+def test_ftle_real_reference_outputs(nb, golden):
+    """float64 outputs of the real numbacs.diagnostics.ftle_grid_2D; tolerance: relative L2 <= 1e-6
+    (north_star); observed ~1e-16 (reciprocal multiplication instead of division)."""
+    T, dx, dy = golden["ftle_args"]
+    for mask, key in ((None, "ftle_out"), (golden["ftle_mask"], "ftle_out_masked")):
+        got = nb.diagnostics.ftle_grid_2D(golden["ftle_in"], T, dx, dy, mask=mask)
+        ref = golden[key]
+        assert np.linalg.norm(got - ref) <= 1e-6 * np.linalg.norm(ref)
+        assert np.abs(got - ref).max() <= 1e-12
+        assert np.array_equal(got == 0.0, ref == 0.0)     # border ring / masked / lambda<=1 zeros
+    out = nb.diagnostics.ftle_grid_2D(golden["ftle_in_contract"], 3.0, 1.0 / 15, 1.0 / 11)
+    assert not out.any()
+
+
+def test_lavd_golden(nb, golden, coords_dg, mask_dg):
+    """tests/test_diagnostics.py:153-173 (trilinear vorticity, odd number of intervals)."""
+    x, y = coords_dg
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    vort = nb.flows.get_callable_scalar_linear(((0.0, 8.0, 4), (0.0, 2.0, 21), (0.0, 1.0, 11)),
+                                               golden["ref_vort"])
+    tspan = np.linspace(0.0, 8.0, 4)
+    fmn = golden["ref_fm_n"].astype(np.float64)
+    lavd = nb.diagnostics.lavd_grid_2D(fmn, tspan, 8.0, vort, X.ravel(), Y.ravel())
+    assert np.allclose(lavd.astype(np.float32), golden["ref_lavd"])
+    lavd_m = nb.diagnostics.lavd_grid_2D(fmn, tspan, 8.0, vort, X.ravel(), Y.ravel(), mask=mask_dg)
+    assert np.allclose(lavd_m.astype(np.float32), apply_mask(golden["ref_lavd"], mask_dg))
+
+
+def test_spline_tables(nb, golden):
+    """tests/test_flows.py:68-139, 208-285 with the GPU prefilter / evaluators."""
+    t = np.array([0.0, 0.1, 0.2])
+    x = np.array([0.0, 0.5, 1.0])
+    T, X, Y = np.meshgrid(t, x, x, indexing="ij")
+    u = np.sin(X) * np.cos(Y) + np.sin(T)
+    v = np.cos(X) * np.sin(Y) + np.cos(T)
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(t, x, x, u, v)
+    assert np.allclose(grid, ((0.0, 0.2, 3), (0.0, 1.0, 3), (0.0, 1.0, 3)))
+    assert Cu.shape == (5, 5, 5)
+    assert np.allclose(Cu, golden["spline_Cu"]) and np.allclose(Cv, golden["spline_Cv"])
+    xi = np.array([0.1, 0.4, 0.7])
+    Ti, Xi, Yi = np.meshgrid(np.array([0.05, 0.12, 0.18]), xi, xi, indexing="ij")
+    pts = np.column_stack((Ti.ravel(), Xi.ravel(), Yi.ravel()))
+    assert np.allclose(nb.flows.get_callable_scalar(grid, Cu)(pts), golden["spline_eval_u"])
+    assert np.allclose(nb.flows.get_callable_scalar(grid, Cv)(pts), golden["spline_eval_v"])
+    assert np.allclose(nb.flows.get_callable_scalar_linear(grid, u)(pts), golden["linear_eval_u"])
+    f1 = nb.flows.get_callable_scalar(grid, Cu)
+    assert abs(f1(pts[5]) - golden["spline_eval_u"][5]) < 1e-8     # single-point call form
+    gs, Cf = nb.flows.get_interp_arrays_scalar(t[::-1], x, x, u[::-1].copy())
+    assert np.allclose(Cf, golden["spline_Cu"])
+
+
+# ------------------------------------------------------------------ RHS level (ulp-scale)
+
+def _gpu_rhs(lib, h, t, y, p):
+    from numbacs_b200 import _lib
+    t, y, p = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, y, p))
+    dy = np.empty_like(y)
+    _lib.check(lib.b200cs_flow_rhs(h, t.ctypes.data, y.ctypes.data, len(t), p.ctypes.data, len(p),
+                                   dy.ctypes.data, None))
+    return dy
+
+
+@pytest.mark.parametrize("name,lo,hi", [("double_gyre", (0, 0), (2, 1)),
+                                        ("bickley_jet", (0, -3), (20, 3)),
+                                        ("abc", (0, 0, 0), (6.28, 6.28, 6.28))])
+def test_rhs_matches_oracle(nb, lib, oracle, name, lo, hi):
+    """Device RHS vs the oracle's (glibc) RHS: a few ulp of the velocity scale."""
+    rng = np.random.default_rng(7)
+    for direction in (1.0, -1.0):
+        h, p, _ = nb.flows.get_predefined_flow(name, int_direction=direction)
+        ho, po, _ = oracle.get_predefined_flow(name, int_direction=direction)
+        assert np.array_equal(p, po)
+        y = rng.uniform(lo, hi, size=(4000, len(lo)))
+        t = rng.uniform(-10, 10, size=4000)
+        g = _gpu_rhs(lib, h, t, y, p)
+        o = np.array([ho.rhs(t[i], y[i], po) for i in range(len(t))])
+        assert np.abs(g - o).max() <= 1e-14 * np.abs(o).max()
+
+
+def test_rhs_velocity_tables(nb, lib, golden):
+    """Device RHS vs the reference's literal velocity tables (tests/test_flows.py:307-425)."""
+    xi = np.array([0.1, 0.4, 0.7])
+    Ti, Xi, Yi = np.meshgrid(np.array([0.05, 0.12, 0.18]), xi, xi, indexing="ij")
+    t, y = Ti.ravel(), np.column_stack((Xi.ravel(), Yi.ravel()))
+    for name, key in (("double_gyre", "dg"), ("bickley_jet", "bickley")):
+        h, p, _ = nb.flows.get_predefined_flow(name)
+        vel = _gpu_rhs(lib, h, t, y, p)
+        assert np.allclose(vel[:, 0], golden[f"vel_{key}_u"])
+        assert np.allclose(vel[:, 1], golden[f"vel_{key}_v"])
+    h, p, _ = nb.flows.get_predefined_flow("abc")
+    g = np.array([0.0, 0.5, 1.0]) + 0.1
+    Ti, Xi, Yi, Zi = np.meshgrid(np.array([0.0, 0.1, 0.2]) + 0.1, g, g, g, indexing="ij")
+    vel = _gpu_rhs(lib, h, Ti.ravel(), np.column_stack((Xi.ravel(), Yi.ravel(), Zi.ravel())), p)
+    for i, c in enumerate("uvw"):
+        assert np.allclose(vel[:, i], golden[f"vel_abc_{c}"])
+
+
+# ------------------------------------------------------------------ flow maps vs the oracle
+
+def test_double_gyre_C1(nb, oracle):
+    """BASELINE config 1: DG 401x201, t0=0, T=-10, dop853 (README example)."""
+    x, y = np.linspace(0, 2, 401), np.linspace(0, 1, 201)
+    f, p, dom = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    fo, po, _ = oracle.get_predefined_flow("double_gyre", int_direction=-1.0)
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x, y, p, info=info)
+    fmo, _, st_o, steps_o, stats_o = oracle.flowmap_grid_2D(fo, 0.0, -10.0, x, y, po, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
+    assert (info["status"] == 1).all() and (st_o == 1).all()
+    assert r["mismatch"] <= max(1, int(1e-6 * r["n"]) + 1), r
+    assert r["max_match"] <= 1e-8, r                      # north_star: 1e-8 x domain size
+    if r["mismatch"] == 0:
+        assert np.array_equal(info["stats"], stats_o)     # same nfev / accepted / rejected totals
+    # FTLE from both flow maps: relative L2 <= 1e-6
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    ft = nb.diagnostics.ftle_grid_2D(fm, -10.0, dx, dy)
+    fto = oracle.ftle_grid_2D(fmo, -10.0, dx, dy)
+    assert np.linalg.norm(ft - fto) <= 1e-6 * np.linalg.norm(fto)
+    # fused call == the two separate calls
+    fm2, ft2 = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -10.0, x, y, p, dx, dy)
+    assert np.array_equal(fm2, fm) and np.array_equal(ft2, ft)
+
+
+def _noise_floor(oracle, flow_o, t0, T, x, y, p, L, k=None, flow_o2=None):
+    """How much the oracle moves under a 1-ulp perturbation (of params[k], or of the coefficient
+    arrays behind flow_o2), over particles whose step counts stay equal."""
+    a, _, _, sa, _ = oracle.flowmap_grid_2D(flow_o, t0, T, x, y, p, full=True)
+    p2 = p.copy()
+    if k is not None:
+        p2[k] = np.nextafter(p2[k], np.inf)
+    b, _, _, sb, _ = oracle.flowmap_grid_2D(flow_o2 or flow_o, t0, T, x, y, p2, full=True)
+    d = (np.abs(a - b) / np.asarray(L)).max(axis=-1)
+    same = (sa == sb).all(axis=-1)
+    return float(d[same].max()), int((~same).sum())
+
+
+def test_bickley_jet(nb, oracle):
+    """BASELINE config 2 (reduced grid): Bickley jet, forward T = 6 (plot_bickley_ftle.py:24)."""
+    f, p, dom = nb.flows.get_predefined_flow("bickley_jet")
+    fo, po, _ = oracle.get_predefined_flow("bickley_jet")
+    L = (dom[0][1] - dom[0][0], dom[1][1] - dom[1][0])
+    x, y = np.linspace(dom[0][0], dom[0][1], 401), np.linspace(-3, 3, 121)
+    # short horizon: plain gate
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 1.0, x, y, p, info=info)
+    fmo, _, _, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 1.0, x, y, po, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, L)
+    assert r["mismatch"] == 0 and r["max_match"] <= 1e-8, r
+    # T = 6: calibrated gate
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 6.0, x, y, p, info=info)
+    fmo, _, st_o, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 6.0, x, y, po, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, L)
+    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 6.0, x, y, po, L, 1)
+    assert (info["status"] == 1).all()
+    assert r["median"] <= 1e-12 and r["p99"] <= 1e-8, r
+    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
+    assert r["mismatch"] <= max(2, 5 * floor_mis), (r, floor_mis)
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    ft = nb.diagnostics.ftle_grid_2D(fm, 6.0, dx, dy)
+    fto = oracle.ftle_grid_2D(fmo, 6.0, dx, dy)
+    same = (info["steps"] == steps_o).all(axis=-1)
+    assert ftle_rel_l2(ft, fto, same) <= 1e-6
+
+
+def test_abc_points(nb, oracle):
+    """3-D state through the point-list entry (flowmap / flowmap_n, integration.py:7-120)."""
+    f, p, _ = nb.flows.get_predefined_flow("abc")
+    fo, po, _ = oracle.get_predefined_flow("abc")
+    pts = np.random.default_rng(1).uniform(0, 2 * np.pi, size=(3000, 3))
+    info = {}
+    fm = nb.integration.flowmap(f, 0.0, 2.0, pts, p, info=info)
+    fmo, _, _, steps_o, _ = oracle.flowmap_pts(fo, 0.0, 2.0, pts, po, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, 2 * np.pi)
+    assert r["mismatch"] <= 1 and r["max_match"] <= 1e-8, r
+    fmn, ts = nb.integration.flowmap_n(f, 0.0, 2.0, pts[:500], p, n=7)
+    fmno, tso = oracle.flowmap_n(fo, 0.0, 2.0, pts[:500], po, n=7)
+    assert np.array_equal(ts, tso)
+    assert np.abs(fmn - fmno).max() <= 1e-8 * 2 * np.pi
+    with pytest.raises(ValueError):
+        nb.integration.flowmap_grid_2D(f, 0.0, 1.0, np.zeros(3), np.zeros(3), p)
+
+
+def _dg_like_field(nt=21, nx=41, ny=31):
+    t, x, y = np.linspace(0, 10, nt), np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    T, X, Y = np.meshgrid(t, x, y, indexing="ij")
+    a = 0.25 * np.sin(0.2 * np.pi * T)
+    b = 1 - 2 * a
+    f = a * X ** 2 + b * X
+    U = -np.pi * 0.1 * np.sin(np.pi * f) * np.cos(np.pi * Y)
+    V = np.pi * 0.1 * np.cos(np.pi * f) * np.sin(np.pi * Y) * (2 * a * X + b)
+    return t, x, y, U, V
+
+
+@pytest.mark.parametrize("mode", ["constant", "linear", "nearest"])
+def test_spline_flow(nb, oracle, mode):
+    """Cubic-spline velocity (get_interp_arrays_2D -> get_flow_2D -> flowmap_grid_2D), particles
+    inside the data grid."""
+    t, x, y, U, V = _dg_like_field()
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(t, x, y, U, V)
+    grid_o, Cuo, Cvo = oracle.get_interp_arrays_2D(t, x, y, U, V)
+    assert np.abs(Cu - Cuo).max() <= 1e-13 and np.abs(Cv - Cvo).max() <= 1e-13
+    f = nb.flows.get_flow_2D(grid, Cu, Cv, extrap_mode=mode)
+    fo = oracle.get_flow_2D(grid_o, Cuo, Cvo, extrap_mode=mode)
+    xg, yg = np.linspace(0.05, 1.95, 101), np.linspace(0.05, 0.95, 51)
+    params = np.array([1.0])
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, xg, yg, params, info=info)
+    fmo, _, _, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 8.0, xg, yg, params, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
+    fo2 = oracle.get_flow_2D(grid_o, Cuo * (1 + 2.3e-16), Cvo, extrap_mode=mode)
+    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 8.0, xg, yg, params, (2.0, 1.0), flow_o2=fo2)
+    assert r["median"] <= 1e-12 and r["p99"] <= 1e-9, r
+    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
+    assert r["mismatch"] <= max(1, 5 * floor_mis), (r, floor_mis)
+    # backward in time with p[0] = -1
+    info = {}
+    fmb = nb.integration.flowmap_grid_2D(f, 8.0, -6.0, xg, yg, -params, info=info)
+    fmbo, _, _, steps_o, _ = oracle.flowmap_grid_2D(fo, 8.0, -6.0, xg, yg, -params, full=True)
+    r = compare_flowmaps(fmb, info, fmbo, steps_o, (2.0, 1.0))
+    assert r["mismatch"] <= 1 and r["p99"] <= 1e-9 and r["max_match"] <= 1e-8, r
+
+
+@pytest.mark.parametrize("spherical", [1, 2])
+def test_spline_flow_spherical(nb, oracle, spherical):
+    """MERRA-shaped (config 3, reduced): lon/lat degrees, spherical=1 ([-180,180)) and 2 ([0,360)),
+    including the Python-modulo longitude wrap (flows.py:162, 205)."""
+    rng = np.random.default_rng(5)
+    t = np.arange(25) * 1.0
+    lon = (-180.0 if spherical == 1 else 0.0) + 5.0 * np.arange(72)
+    lat = -90.0 + 5.0 * np.arange(37)
+    T, LO, LA = np.meshgrid(t, np.deg2rad(lon), np.deg2rad(lat), indexing="ij")
+    U = np.zeros_like(T)
+    V = np.zeros_like(T)
+    for _ in range(4):
+        k, l = rng.integers(1, 4), rng.integers(1, 3)
+        ph, om = rng.uniform(0, 6.28), rng.uniform(0.05, 0.2)
+        U += 40.0 * np.cos(LA) * np.sin(k * LO + om * T + ph) * np.cos(l * LA)
+        V += 25.0 * np.cos(LA) * np.cos(k * LO - om * T + ph) * np.sin(2 * l * LA)
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(t, lon, lat, U, V)
+    f = nb.flows.get_flow_2D(grid, Cu, Cv, spherical=spherical, extrap_mode="linear")
+    fo = oracle.get_flow_2D(grid, Cu, Cv, spherical=spherical, extrap_mode="linear")
+    lo0 = -100.0 if spherical == 1 else 200.0
+    xg, yg = lo0 + 0.5 * np.arange(120), -5.0 + 0.5 * np.arange(80)
+    params = np.array([-1.0])
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 20.0, -18.0, xg, yg, params, info=info)
+    fmo, _, _, steps_o, _ = oracle.flowmap_grid_2D(fo, 20.0, -18.0, xg, yg, params, full=True)
+    r = compare_flowmaps(fm, info, fmo, steps_o, (360.0, 180.0))
+    assert r["mismatch"] <= 1 and r["p99"] <= 1e-9 and r["max_match"] <= 1e-8, r
+    # a particle that crosses the wrap longitude is handled like the reference's % operator
+    edge = 179.9 if spherical == 1 else 359.9
+    pts = np.array([[edge, 10.0], [edge + 0.3, -20.0], [edge - 360.0, 30.0]])
+    a = nb.integration.flowmap(f, 0.0, 12.0, pts, np.array([1.0]))
+    b = oracle.flowmap(fo, 0.0, 12.0, pts, np.array([1.0]))
+    assert np.abs(a - b).max() <= 1e-8 * 360.0
+
+
+def test_flowmap_n_dense_output(nb, oracle):
+    """n = 50 output times (default of flowmap_n_grid_2D): dense-output rows vs the oracle."""
+    x, y = np.linspace(0, 2, 64), np.linspace(0, 1, 33)
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fo, po, _ = oracle.get_predefined_flow("double_gyre")
+    info = {}
+    fmn, ts = nb.integration.flowmap_n_grid_2D(f, 1.0, 9.0, x, y, p, info=info)
+    fmno, tso, _, steps_o, stats_o = oracle.flowmap_n_grid_2D(fo, 1.0, 9.0, x, y, po, full=True)
+    assert fmn.shape == (64, 33, 50, 2) and np.array_equal(ts, tso)
+    same = (info["steps"] == steps_o).all(axis=-1)
+    assert (~same).sum() <= 1
+    assert np.abs(fmn - fmno)[same].max() <= 1e-8
+    if same.all():
+        assert np.array_equal(info["stats"], stats_o)      # incl. the 3 extra RHS per dense step
+    # backward with p0 = -1: tspan is the physical time (integration.py:533)
+    _, pb, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    fmb, tsb = nb.integration.flowmap_n_grid_2D(f, 0.0, -5.0, x[:8], y[:8], pb, n=11)
+    fmbo, tsbo = oracle.flowmap_n_grid_2D(fo, 0.0, -5.0, x[:8], y[:8], pb, n=11)
+    assert np.array_equal(tsb, tsbo) and np.allclose(tsb, np.linspace(0, -5, 11))
+    assert np.abs(fmb - fmbo).max() <= 1e-8
+
+
+def test_lavd_cubic_spline(nb, oracle):
+    """LAVD with the cubic-spline vorticity (the example's path, plot_qge_elliptic_lcs.py:56-88),
+    even and odd numbers of Simpson intervals, periodic wrapping, mask."""
+    t, x, y, U, V = _dg_like_field(nt=17, nx=33, ny=25)
+    rng = np.random.default_rng(2)
+    T, X, Y = np.meshgrid(t, x, y, indexing="ij")
+    vort = np.sin(3 * X + 0.3 * T) * np.cos(2 * Y) + 0.1 * rng.normal(size=T.shape)
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(t, x, y, U, V)
+    f = nb.flows.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")
+    gw, Cw = nb.flows.get_interp_arrays_scalar(t, x, y, vort)
+    w = nb.flows.get_callable_scalar(gw, Cw, extrap_mode="linear")
+    wo = oracle.get_callable_scalar(gw, Cw, extrap_mode="linear")
+    xg, yg = np.linspace(0.1, 1.9, 40), np.linspace(0.1, 0.9, 24)
+    Xg, Yg = np.meshgrid(xg, yg, indexing="ij")
+    mask = rng.random((40, 24)) < 0.1
+    for n in (12, 13):
+        fmn, ts = nb.integration.flowmap_n_grid_2D(f, 1.0, 6.0, xg, yg, np.array([1.0]), n=n)
+        for px, py in ((0.0, 0.0), (1.5, 0.0), (0.0, 0.7), (1.5, 0.7)):
+            got = nb.diagnostics.lavd_grid_2D(fmn, ts, 6.0, w, Xg.ravel(), Yg.ravel(), px, py, mask=mask)
+            ref = oracle.lavd_grid_2D(fmn, ts, 6.0, wo, Xg.ravel(), Yg.ravel(), px, py, mask=mask)
+            assert np.array_equal(got == 0.0, ref == 0.0)
+            assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    with pytest.raises(NotImplementedError):
+        nb.diagnostics.lavd_grid_2D(fmn, ts, 6.0, lambda p: p, Xg.ravel(), Yg.ravel())
+
+
+# ------------------------------------------------------------------ API behaviour / edge cases
+
+def test_unknown_funcptr_is_rejected(nb):
+    with pytest.raises(NotImplementedError, match="no CPU fallback"):
+        nb.integration.flowmap_grid_2D(140234567, 0.0, 1.0, np.zeros(2), np.zeros(2), np.ones(6))
+
+
+def test_empty_and_degenerate_inputs(nb):
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 1.0, np.zeros(0), np.linspace(0, 1, 5), p)
+    assert fm.shape == (0, 5, 2)
+    assert nb.integration.flowmap(f, 0.0, 1.0, np.zeros((0, 2)), p).shape == (0, 2)
+    # T = 0: the flow map is the identity
+    x, y = np.linspace(0, 2, 7), np.linspace(0, 1, 5)
+    fm = nb.integration.flowmap_grid_2D(f, 3.0, 0.0, x, y, p)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    assert np.array_equal(fm, np.stack([X, Y], axis=-1))
+    # all masked
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 1.0, x, y, p, mask=np.ones((7, 5), bool))
+    assert not fm.any()
+    # tiny FTLE grids are all border
+    assert not nb.diagnostics.ftle_grid_2D(np.random.rand(2, 2, 2), 1.0, 0.1, 0.1).any()
+    assert nb.diagnostics.ftle_grid_2D(np.random.rand(1, 6, 2), 1.0, 0.1, 0.1).shape == (1, 6)
+    # ragged sizes that are not multiples of the block / tile sizes
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 2.0, np.linspace(0, 2, 131), np.linspace(0, 1, 67), p, info=info)
+    assert fm.shape == (131, 67, 2) and (info["status"] == 1).all()
+    ft = nb.diagnostics.ftle_grid_2D(fm, 2.0, 2 / 130, 1 / 66)
+    assert ft.shape == (131, 67) and not ft[0].any() and not ft[:, -1].any() and ft[1:-1, 1:-1].any()
+
+
+def test_torch_tensors_stay_on_device(nb):
+    torch = pytest.importorskip("torch")
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    x = torch.linspace(0, 2, 96, dtype=torch.float64, device="cuda")
+    y = torch.linspace(0, 1, 48, dtype=torch.float64, device="cuda")
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, -4.0, x, y, p)
+    assert isinstance(fm, torch.Tensor) and fm.is_cuda and fm.shape == (96, 48, 2)
+    ft = nb.diagnostics.ftle_grid_2D(fm, -4.0, 2 / 95, 1 / 47)
+    assert ft.is_cuda
+    fm_h = nb.integration.flowmap_grid_2D(f, 0.0, -4.0, x.cpu().numpy(), y.cpu().numpy(), p)
+    assert np.array_equal(fm.cpu().numpy(), fm_h)            # same kernel, same bits
+    ft_h = nb.diagnostics.ftle_grid_2D(fm_h, -4.0, 2 / 95, 1 / 47)
+    assert np.array_equal(ft.cpu().numpy(), ft_h)
+    # a strided / offset view still works (falls back to 8-byte stores / gets copied)
+    fm2 = nb.integration.flowmap_grid_2D(f, 0.0, -4.0, x[1:], y, p)
+    assert np.array_equal(fm2.cpu().numpy(), fm_h[1:])
+
+
+def test_large_grid_properties(nb):
+    """Size-independent properties at a size the CPU oracle would need minutes for (2048 x 1024):
+    invariance of the closed DG domain, per-particle determinism (a sub-sampled grid and a point
+    list give the same bits as the full grid), forward/backward round trip, FTLE border zeros."""
+    torch = pytest.importorskip("torch")
+    nx, ny = 2048, 1024
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x, y, p, info=info)
+    assert (info["status"] == 1).all()
+    assert fm[..., 0].min() >= -1e-9 and fm[..., 0].max() <= 2 + 1e-9
+    assert fm[..., 1].min() >= -1e-9 and fm[..., 1].max() <= 1 + 1e-9
+    sub = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x[::64], y[::32], p)
+    assert np.array_equal(sub, fm[::64, ::32])
+    X, Y = np.meshgrid(x[5::128], y[3::64], indexing="ij")
+    pts = np.column_stack((X.ravel(), Y.ravel()))
+    assert np.array_equal(nb.integration.flowmap(f, 0.0, -10.0, pts, p).reshape(X.shape + (2,)),
+                          fm[5::128, 3::64])
+    # round trip with tight tolerances
+    _, pf, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=1.0)
+    back = nb.integration.flowmap(f, 0.0, -10.0, pts, p, rtol=1e-11, atol=1e-13)
+    again = nb.integration.flowmap(f, -10.0, 10.0, back, pf, rtol=1e-11, atol=1e-13)
+    assert np.abs(again - pts).max() < 1e-6
+    ft = nb.diagnostics.ftle_grid_2D(fm, -10.0, x[1] - x[0], y[1] - y[0])
+    assert not ft[0].any() and not ft[-1].any() and not ft[:, 0].any() and not ft[:, -1].any()
+    assert ft.min() >= 0.0 and 0.3 < ft.max() < 1.5
+    # mean accepted / rejected steps as the survey measured for C1 (13.0 / 3.4)
+    acc, rej = info["stats"][1] / (nx * ny), info["stats"][2] / (nx * ny)
+    assert 12.0 < acc < 14.5 and 2.5 < rej < 4.5
