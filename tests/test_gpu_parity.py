@@ -478,8 +478,10 @@ def test_large_grid_properties(nb):
     info = {}
     fm = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x, y, p, info=info)
     assert (info["status"] == 1).all()
-    assert fm[..., 0].min() >= -1e-9 and fm[..., 0].max() <= 2 + 1e-9
-    assert fm[..., 1].min() >= -1e-9 and fm[..., 1].max() <= 1 + 1e-9
+    # the walls are invariant for the exact flow; the solver's own truncation error (~1e-4 at
+    # rtol 1e-6) lets boundary particles drift by that much
+    assert fm[..., 0].min() >= -1e-3 and fm[..., 0].max() <= 2 + 1e-3
+    assert fm[..., 1].min() >= -1e-3 and fm[..., 1].max() <= 1 + 1e-3
     sub = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x[::64], y[::32], p)
     assert np.array_equal(sub, fm[::64, ::32])
     X, Y = np.meshgrid(x[5::128], y[3::64], indexing="ij")
