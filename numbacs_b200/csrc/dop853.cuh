@@ -2,17 +2,28 @@
 //
 // Replaces numbalsoda.dop853(funcptr, u0, t_eval, rtol, atol, data) as called from
 // /root/reference/src/numbacs/integration.py:49, 108, 169, 520.  The step-size controller is
-// Hairer's classical one (dop853.f): safe 0.9, fac1 0.333, fac2 6, beta 0, facold 1e-4, hinit with
-// iord 8, "no growth after a reject", last step when x + 1.01 h passes xend; one continuous
-// integration over the output times with 7th-order dense output (contd8) at interior times.
-// Parity with the reference requires the SAME accept/reject sequence per particle, so nothing in
-// the controller is "improved".
+// Hairer's classical one (dop853.f): safe 0.9, fac1 0.333, fac2 6, beta 0, hinit with iord 8,
+// "no growth after a reject", last step when x + 1.01 h passes xend; one continuous integration
+// over the output times with 7th-order dense output (contd8) at interior times.  Parity with the
+// reference requires the SAME accept/reject sequence per particle, so nothing in the controller
+// is "improved": every particle keeps its own x, h and accept/reject history.
 //
-// GPU shape: every lane owns its particle, its step size and its accept/reject decisions; one
-// loop iteration is one step ATTEMPT (12 stages, error estimate, predicated state update), so a
-// warp stays converged except for the FSAL evaluation of rejected lanes and the tail where lanes
-// need different numbers of attempts.  All tableau coefficients are compile-time constants (the
-// zero entries vanish); the stage slopes live in registers.
+// GPU shape.  Every lane owns its particle, its step size and its decisions; one loop iteration
+// is one step ATTEMPT (12 stages, error estimate, predicated state update), so a warp stays
+// converged except for the FSAL evaluation of rejected lanes and the tail where lanes need
+// different numbers of attempts.  The twelve stages are fully unrolled with the stage slopes in
+// registers and the tableau's zero entries removed at compile time.
+//
+// What was measured on B200 before settling on this shape (profiles/README.md has the numbers):
+// the kernel is FP64-ISSUE bound -- one DFMA per two cycles per SM sub-partition (8.3-cycle
+// dependent latency), FP64 instructions cannot take constant-bank operands on sm_100, and with
+// ~5 resident warps per sub-partition the dependent chains of one particle are what limits the
+// issue rate.  Variants with 2 or 4 particles per thread and the slopes in shared memory (more
+// ILP, coefficient fetches shared between particles, a single RHS copy in the instruction stream)
+// executed MORE instructions per particle and were 5-40 % slower; an out-of-line RHS removed the
+// instruction-cache stalls of the 65 KB unrolled body but its call overhead cost as much.  What
+// did pay: a leaner RHS, and batching the time-only part of the RHS over the stage times of a
+// step (known up front), which shortens the dependent chain of every stage.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -34,24 +45,38 @@ namespace detail {
 // is <= 1 ulp and only scales the next step size)
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
 
+// yy = y + h * sum_j a(S,j) K_j   (j ascending, zero entries skipped at compile time)
 template <int S, int N, int... J>
 __device__ __forceinline__ void stage_arg(double (&yy)[N], const double (&y)[N], double h,
                                           const double (&K)[17][N], std::integer_sequence<int, J...>) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double acc = 0.0;
-        // sum_j a(S,j) * K[j][i], j ascending, zero entries skipped at compile time
         ((dop::a(S, J + 1) != 0.0 ? (void)(acc = fma(dop::kTab.a[S][J + 1], K[J + 1][i], acc)) : (void)0), ...);
         yy[i] = fma(h, acc, y[i]);
     }
 }
 
+// stage S: K_S = f(x + c_S h, y + h sum a_Sj K_j); `aux` is the precomputed time-only part
 template <int S, class Rhs, int N>
-__device__ __forceinline__ void do_stage(const Rhs &rhs, double x, double h, const double (&y)[N],
+__device__ __forceinline__ void do_stage(const Rhs &rhs, double aux, double x, double h, const double (&y)[N],
                                          double (&K)[17][N]) {
     double yy[N];
     stage_arg<S, N>(yy, y, h, K, std::make_integer_sequence<int, S - 1>{});
-    rhs(fma(dop::kTab.c[S], h, x), yy, K[S]);
+    rhs.eval(aux, fma(dop::kTab.c[S], h, x), yy, K[S]);
+}
+
+// time-only part of the RHS at the stage times S0 .. S0+M-1 of the step (x, h), M chains at once
+template <int S0, int M, class Rhs>
+__device__ __forceinline__ void stage_aux(const Rhs &rhs, double x, double h, double (&aux)[17]) {
+    if constexpr (Rhs::kAux != 0) {
+        double t[M], a[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) t[m] = fma(dop::kTab.c[S0 + m], h, x);
+        rhs.template time_part<M>(t, a);
+#pragma unroll
+        for (int m = 0; m < M; ++m) aux[S0 + m] = a[m];
+    }
 }
 
 template <int R, int N, int... J>
@@ -83,10 +108,10 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
     constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
     constexpr int kNmax = 100000;
     double K[17][N];  // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages
+    double aux[17];   // time-only part of the RHS per stage (flows that have one)
     double x = x0;
     const double posneg = (xend - x0) < 0.0 ? -1.0 : 1.0;
     const double hmax = fabs(xend - x0);
-    double facold = 1.0e-4;
     bool last = false, reject = false;
     int nstep = 0;
     int iout = 1;  // next output row
@@ -95,7 +120,11 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
     double tnext = 0.0;
     if (DENSE) tnext = t_out(1);
 
-    rhs(x, y, K[1]);
+    {
+        double t1[1] = {x}, a1[1] = {0.0};
+        if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
+        rhs.eval(a1[0], x, y, K[1]);
+    }
     // ---- hinit (iord = 8)
     double h;
     {
@@ -112,7 +141,9 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
         double y1[N], f1[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) y1[i] = fma(h, K[1][i], y[i]);
-        rhs(x + h, y1, f1);
+        double t1[1] = {x + h}, a1[1] = {0.0};
+        if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
+        rhs.eval(a1[0], x + h, y1, f1);
         double der2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -136,24 +167,29 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
             last = true;
         }
         ++nstep;
-        detail::do_stage<2>(rhs, x, h, y, K);
-        detail::do_stage<3>(rhs, x, h, y, K);
-        detail::do_stage<4>(rhs, x, h, y, K);
-        detail::do_stage<5>(rhs, x, h, y, K);
-        detail::do_stage<6>(rhs, x, h, y, K);
-        detail::do_stage<7>(rhs, x, h, y, K);
-        detail::do_stage<8>(rhs, x, h, y, K);
-        detail::do_stage<9>(rhs, x, h, y, K);
-        detail::do_stage<10>(rhs, x, h, y, K);
-        detail::do_stage<11>(rhs, x, h, y, K);
+        // the stage times x + c_s h are known now: the time-only part of the RHS is evaluated for
+        // four stages at a time (four independent chains), off the stages' critical path
+        detail::stage_aux<2, 4>(rhs, x, h, aux);
+        detail::do_stage<2>(rhs, aux[2], x, h, y, K);
+        detail::do_stage<3>(rhs, aux[3], x, h, y, K);
+        detail::do_stage<4>(rhs, aux[4], x, h, y, K);
+        detail::do_stage<5>(rhs, aux[5], x, h, y, K);
+        detail::stage_aux<6, 4>(rhs, x, h, aux);
+        detail::do_stage<6>(rhs, aux[6], x, h, y, K);
+        detail::do_stage<7>(rhs, aux[7], x, h, y, K);
+        detail::do_stage<8>(rhs, aux[8], x, h, y, K);
+        detail::do_stage<9>(rhs, aux[9], x, h, y, K);
+        detail::stage_aux<10, 3>(rhs, x, h, aux);  // c12 = 1: aux[12] also serves the FSAL slope
+        detail::do_stage<10>(rhs, aux[10], x, h, y, K);
+        detail::do_stage<11>(rhs, aux[11], x, h, y, K);
         const double xph = x + h;
         {   // stage 12 is evaluated at x + h exactly
             double yy[N];
             detail::stage_arg<12, N>(yy, y, h, K, std::make_integer_sequence<int, 11>{});
-            rhs(xph, yy, K[12]);
+            rhs.eval(aux[12], xph, yy, K[12]);
         }
         // 8th-order slope, candidate state, and the two embedded error estimates
-        double kb[N], y5[N];
+        double y5[N];
         double err = 0.0, err2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -165,7 +201,6 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
             s = fma(dop::kTab.b[10], K[10][i], s);
             s = fma(dop::kTab.b[11], K[11][i], s);
             s = fma(dop::kTab.b[12], K[12][i], s);
-            kb[i] = s;
             y5[i] = fma(h, s, y[i]);
             const double sk = fma(rtol, fmax(fabs(y[i]), fabs(y5[i])), atol);
             double e3 = fma(-dop::kTab.bhh[0], K[1][i], s);
@@ -192,9 +227,8 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
         double hnew = h / fac;
         if (err <= 1.0) {
             // ---- accepted
-            facold = fmax(err, 1.0e-4);
             ++cnt.accepted;
-            rhs(xph, y5, K[13]);  // first-same-as-last slope
+            rhs.eval(aux[12], xph, y5, K[13]);  // first-same-as-last slope, same time as stage 12
             if (DENSE) {
                 if (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0) {
                     ++cnt.dense;
@@ -208,9 +242,10 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
                         rc[2][i] = bspl;
                         rc[3][i] = ydiff - h * K[13][i] - bspl;
                     }
-                    detail::do_stage<14>(rhs, x, h, y, K);
-                    detail::do_stage<15>(rhs, x, h, y, K);
-                    detail::do_stage<16>(rhs, x, h, y, K);
+                    detail::stage_aux<14, 3>(rhs, x, h, aux);
+                    detail::do_stage<14>(rhs, aux[14], x, h, y, K);
+                    detail::do_stage<15>(rhs, aux[15], x, h, y, K);
+                    detail::do_stage<16>(rhs, aux[16], x, h, y, K);
 #pragma unroll
                     for (int i = 0; i < N; ++i) {
                         rc[4][i] = h * detail::dense_row<4, N>(K, i, std::make_integer_sequence<int, 16>{});
@@ -258,7 +293,6 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
         h = hnew;
     }
     if (DENSE && status == B200CS_ST_OK && n_out >= 2) sink(n_out - 1, y);
-    (void)facold;
     return status;
 }
 

@@ -35,10 +35,11 @@ __global__ void rhs_kernel(const __grid_constant__ RhsParams P, const double *__
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= npts) return;
     const Rhs rhs(P);
-    double yy[N], d[N];
+    double yy[N], d[N], tt[1] = {t[q]}, aux[1] = {0.0};
 #pragma unroll
     for (int i = 0; i < N; ++i) yy[i] = y[q * N + i];
-    rhs(t[q], yy, d);
+    if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(tt, aux);
+    rhs.eval(aux[0], tt[0], yy, d);
 #pragma unroll
     for (int i = 0; i < N; ++i) dy[q * N + i] = d[i];
 }

@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kBlock) flowmap_kernel(const __grid_constant__
     }
     if (A.stats) {
         const int nstep = cnt.accepted + cnt.rejected;
-        unsigned long long nfev = active && (A.xend != A.x0) ? 2ull + 11ull * nstep + cnt.accepted + 3ull * cnt.dense : 0ull;
+        unsigned long long nfev =
+            active && (A.xend != A.x0) ? 2ull + 11ull * nstep + cnt.accepted + 3ull * cnt.dense : 0ull;
         unsigned long long acc = cnt.accepted, rej = cnt.rejected;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__(kBlock) flowmap_kernel(const __grid_constant__
             acc += __shfl_down_sync(0xffffffffu, acc, o);
             rej += __shfl_down_sync(0xffffffffu, rej, o);
         }
-        if ((threadIdx.x & 31) == 0) {
+        if ((threadIdx.x & 31) == 0 && nfev) {
             atomicAdd(&A.stats[0], nfev);
             atomicAdd(&A.stats[1], acc);
             atomicAdd(&A.stats[2], rej);
