@@ -21,9 +21,9 @@
 // issue rate.  Variants with 2 or 4 particles per thread and the slopes in shared memory (more
 // ILP, coefficient fetches shared between particles, a single RHS copy in the instruction stream)
 // executed MORE instructions per particle and were 5-40 % slower; an out-of-line RHS removed the
-// instruction-cache stalls of the 65 KB unrolled body but its call overhead cost as much.  What
-// did pay: a leaner RHS, and batching the time-only part of the RHS over the stage times of a
-// step (known up front), which shortens the dependent chain of every stage.
+// instruction-cache stalls of the 62 KB unrolled body but its call overhead cost more (567 vs
+// 598 M points/s).  What did pay: a leaner RHS, and batching the time-only part of the RHS over
+// the stage times of a step (known up front), which shortens the dependent chain of every stage.
 #pragma once
 #include <cuda_runtime.h>
 
