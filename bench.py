@@ -239,7 +239,7 @@ def run_b200(args):
 
     # ---- device-timed region
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
     sync_all()
     t_wall = time.perf_counter()
     for k in range(K):
@@ -248,15 +248,16 @@ def run_b200(args):
         ev[k][1].record(stream)
         if world > 1:
             exchange_halo_rows(slab, has_lo, has_hi, rank)
-        k_ftle()
         ev[k][2].record(stream)
+        k_ftle()
+        ev[k][3].record(stream)
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall
-    total_ms = sum(ev[k][0].elapsed_time(ev[k][2]) for k in range(K))
-    # back-to-back steps on one stream: event span first->last equals the sum of the step spans
-    span_ms = ev[0][0].elapsed_time(ev[K - 1][2])
+    # back-to-back steps on one stream: the span first->last event covers exactly K steps
+    span_ms = ev[0][0].elapsed_time(ev[K - 1][3])
     fm_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]))
-    ft_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))
+    halo_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))  # incl. waiting for the neighbour
+    ft_ms = float(np.mean([ev[k][2].elapsed_time(ev[k][3]) for k in range(K)]))
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if sampler else None
@@ -280,13 +281,13 @@ def run_b200(args):
     checksum = float(ftle_host.sum()) if rows else 0.0   # device->host result actually read
 
     # ---- max over ranks
-    t = torch.tensor([span_ms, e2e_ms, fm_ms, ft_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([span_ms, e2e_ms, fm_ms, ft_ms, halo_ms], dtype=torch.float64, device="cuda")
     agg = torch.cat([torch.tensor(st, dtype=torch.float64, device="cuda"),
                      torch.tensor([checksum], dtype=torch.float64, device="cuda")])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    span_ms, e2e_ms, fm_ms, ft_ms = t.tolist()
+    span_ms, e2e_ms, fm_ms, ft_ms, halo_ms = t.tolist()
     nfev, nacc, nrej, checksum = agg.tolist()
 
     if rank == 0:
@@ -349,6 +350,7 @@ def run_b200(args):
                               "kernel_ms": ft_ms, "peak_source": hbm_src, "bytes_per_point": 24},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "halo_exchange_ms": halo_ms if world > 1 else 0.0,
             "wall_ms_per_step": t_wall / K * 1e3,
             "ftle_checksum": checksum,
             "fp64_peak_tflops_measured": fp64_peak,

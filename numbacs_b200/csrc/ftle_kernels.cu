@@ -58,28 +58,31 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
     const long long j = (long long)blockIdx.x * kCols + threadIdx.x;
     const long long i0 = row_lo + (long long)blockIdx.y * kRows;
     if (j >= ny || i0 >= row_hi) return;
+    // everything below the strip origin is 32-bit arithmetic (the launcher checks that a strip of
+    // kRows + 3 rows fits in 2^31 elements); only the three base pointers are 64-bit
     const int rows = (int)((row_hi - i0 < kRows) ? (row_hi - i0) : kRows);
+    const int avail = (int)((nx - i0 < kRows + 3) ? (nx - i0) : (kRows + 3));  // rows i0 .. i0+avail-1 exist
+    const int nyi = (int)ny;
     const bool col_border = (j == 0) || (j == ny - 1);
     const int offl = (j > 0) ? -1 : 0, offr = (j < ny - 1) ? 1 : 0;
+    const int r_first_border = (lo_is_border && i0 == 0) ? 0 : -1;
+    const int r_last_border = (hi_is_border && nx - 1 - i0 < kRows) ? (int)(nx - 1 - i0) : -1;
     const double2 zero = make_double2(0.0, 0.0);
-    // pc walks down column j; all further addressing is pointer increments (no 64-bit multiplies)
     const double2 *pc = fm + i0 * ny + j;
     const uint8_t *pm = mask ? mask + i0 * ny + j : nullptr;
     double *po = out + (i0 - row_lo) * ny + j;
     // three live rows in registers plus two rows of read-ahead
-    double2 dn = (i0 >= 1) ? __ldg(pc - ny) : zero;
+    double2 dn = (i0 >= 1) ? __ldg(pc - nyi) : zero;
     double2 mid = __ldg(pc);
-    double2 up = (i0 + 1 < nx) ? __ldg(pc + ny) : zero;
-    double2 up2 = (i0 + 2 < nx && rows > 1) ? __ldg(pc + 2 * ny) : zero;
-    const long long ny3 = 3 * ny;
+    double2 up = (1 < avail) ? __ldg(pc + nyi) : zero;
+    double2 up2 = (2 < avail) ? __ldg(pc + 2 * nyi) : zero;
+    int o = 0;  // element offset of row i0 + r from the strip origin
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
-        const long long i = i0 + r;
-        const double2 up3 = (r + 2 < rows && i + 3 < nx) ? __ldg(pc + ny3) : zero;  // read-ahead
-        const double2 lf = __ldg(pc + offl), rt = __ldg(pc + offr);
-        const bool skip = col_border || (i == 0 && lo_is_border) || (i == nx - 1 && hi_is_border) ||
-                          (pm != nullptr && *pm != 0);
-        double val = 0.0;
+        const double2 up3 = (r + 3 < avail) ? __ldg(pc + (o + 3 * nyi)) : zero;  // read-ahead
+        const double2 lf = __ldg(pc + (o + offl)), rt = __ldg(pc + (o + offr));
+        bool skip = col_border || r == r_first_border || r == r_last_border;
+        if (pm != nullptr) skip |= (pm[o] != 0);
         const double dxdx = (up.x - dn.x) * inv2dx;
         const double dxdy = (rt.x - lf.x) * inv2dy;
         const double dydx = (up.y - dn.y) * inv2dx;
@@ -90,17 +93,16 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
         const double amd = a - d;
         const double disc = sqrt(fma(amd, amd, 4.0 * (off * off)));
         const double max_eig = 0.5 * ((a + d) + disc);
+        double val = 0.0;
         // max_eig > 1 also filters NaN; huge values (overflowed gradients) go through libm
         if (!skip && max_eig > 1.0)
             val = scaling * (max_eig < 1.0e300 ? log_table(max_eig, tab) : log(max_eig));
-        *po = val;
+        po[o] = val;
         dn = mid;
         mid = up;
         up = up2;
         up2 = up3;
-        pc += ny;
-        po += ny;
-        if (pm) pm += ny;
+        o += nyi;
     }
 }
 
@@ -133,6 +135,7 @@ void launch_ftle(const double *fm, long long nx, long long ny, double T, double 
     const double scaling = 1.0 / (2.0 * fabs(T));
     const dim3 grid((unsigned)((ny + kCols - 1) / kCols), (unsigned)((row_hi - row_lo + kRows - 1) / kRows));
     B2_REQUIRE(grid.y <= 65535u, "too many rows for one FTLE launch (%lld)", row_hi - row_lo);
+    B2_REQUIRE(ny * (kRows + 4) < 2147483647LL, "ny too large for the FTLE kernel (%lld)", ny);
     ftle_kernel<<<grid, kCols, 0, s>>>(reinterpret_cast<const double2 *>(fm), nx, ny, scaling,
                                        1.0 / (2.0 * dx), 1.0 / (2.0 * dy), mask, out, row_lo, row_hi,
                                        lo_is_border ? 1 : 0, hi_is_border ? 1 : 0);
