@@ -22,14 +22,21 @@
 // ILP, coefficient fetches shared between particles, a single RHS copy in the instruction stream)
 // executed MORE instructions per particle and were 5-40 % slower; an out-of-line RHS removed the
 // instruction-cache stalls of the 62 KB unrolled body but its call overhead cost more (567 vs
-// 598 M points/s).  What did pay: a leaner RHS, and batching the time-only part of the RHS over
-// the stage times of a step (known up front), which shortens the dependent chain of every stage.
+// 598 M points/s).  What did pay: a leaner RHS; batching the time-only part of the RHS over the
+// stage times of a step (known up front), which shortens the dependent chain of every stage; and
+// LOCKSTEP blocks -- one 640-thread block per SM that meets at a barrier every 8 attempts, so its
+// 20 warps walk the unrolled body together and share its instruction-cache footprint (stall on
+// instruction fetch 19 % -> 1 %; a barrier on EVERY attempt gives the gain back as barrier wait).
 #pragma once
 #include <cuda_runtime.h>
 
 #include <utility>
 
 #include "dop853_tableau.cuh"
+
+#ifndef B200CS_SYNC_EVERY
+#define B200CS_SYNC_EVERY 8
+#endif
 
 namespace b200cs {
 
@@ -100,13 +107,14 @@ struct NoSink {
 //   n_out  >= 2 : output times are t_k = p0 * (t0 + k*step), k = 0..n_out-1 (last = p0*(t0+T)),
 //                 rows 1..n_out-1 go to `sink`
 // Returns B200CS_ST_OK / _NMAX / _HSMALL; y holds the state reached.
-template <bool DENSE, class Rhs, int N, class Sink>
-__device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], double x0, double xend,
+template <bool DENSE, bool LOCKSTEP, class Rhs, int N, class Sink>
+__device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, double (&y)[N], double x0, double xend,
                                                 double rtol, double atol, int n_out, double out_p0,
                                                 double out_t0, double out_step, Sink &&sink,
                                                 StepCounts &cnt) {
     constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
     constexpr int kNmax = 100000;
+    constexpr int kSyncEvery = B200CS_SYNC_EVERY;
     double K[17][N];  // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages
     double aux[17];   // time-only part of the RHS per stage (flows that have one)
     double x = x0;
@@ -119,14 +127,20 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
     auto t_out = [&](int k) { return __dmul_rn(out_p0, __dadd_rn(out_t0, __dmul_rn((double)k, out_step))); };
     double tnext = 0.0;
     if (DENSE) tnext = t_out(1);
+    // LOCKSTEP: every thread of the block calls this function (inactive ones idle) and the block
+    // meets at a barrier before each step attempt, so all its warps walk the large unrolled body
+    // together and share its instruction-cache footprint.
+    bool alive = active;
+    double h = 0.0;
+    int status = active ? B200CS_ST_OK : B200CS_ST_MASKED;
 
+    if (alive) {
     {
         double t1[1] = {x}, a1[1] = {0.0};
         if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
         rhs.eval(a1[0], x, y, K[1]);
     }
     // ---- hinit (iord = 8)
-    double h;
     {
         double dnf = 0.0, dny = 0.0;
 #pragma unroll
@@ -157,11 +171,19 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
                                              : detail::pow_eighth(0.01 / der12);
         h = fmin(100.0 * fabs(h), fmin(h1, hmax)) * posneg;
     }
+    }  // if (alive)
 
-    int status = B200CS_ST_OK;
-    for (;;) {
-        if (nstep > kNmax) { status = B200CS_ST_NMAX; break; }
-        if (0.1 * fabs(h) <= fabs(x) * kURound) { status = B200CS_ST_HSMALL; break; }
+    for (int it = 0;; ++it) {
+        if (LOCKSTEP) {
+            // re-align the block every kSyncEvery attempts (warps drift apart only slowly); the
+            // loop is left at a barrier, by all threads together, once nobody is alive
+            if ((it % kSyncEvery) == 0 && !__syncthreads_or(alive ? 1 : 0)) break;
+        } else if (!alive) {
+            break;
+        }
+        if (alive) do {
+        if (nstep > kNmax) { status = B200CS_ST_NMAX; alive = false; break; }
+        if (0.1 * fabs(h) <= fabs(x) * kURound) { status = B200CS_ST_HSMALL; alive = false; break; }
         if ((x + 1.01 * h - xend) * posneg > 0.0) {
             h = xend - x;
             last = true;
@@ -279,7 +301,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
                 y[i] = y5[i];
             }
             x = xph;
-            if (last) break;
+            if (last) { alive = false; break; }
             if (fabs(hnew) > hmax) hnew = posneg * hmax;
             if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
             reject = false;
@@ -291,6 +313,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, double (&y)[N], 
             ++cnt.rejected;
         }
         h = hnew;
+        } while (0);
     }
     if (DENSE && status == B200CS_ST_OK && n_out >= 2) sink(n_out - 1, y);
     return status;

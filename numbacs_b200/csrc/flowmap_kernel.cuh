@@ -16,7 +16,22 @@ namespace b200cs {
 
 namespace {
 
-constexpr int kBlock = 128;
+// Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow.
+// The final-time double-gyre kernel (the headline workload) runs ONE 640-thread block per SM
+// (20 warps at <= 96 registers) with a block barrier before every step attempt: all 20 warps walk
+// the 62 KB unrolled body together, which removes most of its instruction-cache misses.
+template <class Rhs, bool DENSE>
+struct KernelShape {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = 1;
+    static constexpr bool kLockstep = false;
+};
+template <>
+struct KernelShape<DoubleGyre, false> {
+    static constexpr int kThreads = 640;
+    static constexpr int kMinBlocks = 1;
+    static constexpr bool kLockstep = true;
+};
 
 template <int N>
 struct RowSink {
@@ -33,8 +48,11 @@ struct RowSink {
 };
 
 template <class Rhs, bool DENSE, bool GRID>
-__global__ void __launch_bounds__(kBlock) flowmap_kernel(const __grid_constant__ IntegArgs A) {
+__global__ void __launch_bounds__(KernelShape<Rhs, DENSE>::kThreads, KernelShape<Rhs, DENSE>::kMinBlocks)
+flowmap_kernel(const __grid_constant__ IntegArgs A) {
     constexpr int N = Rhs::N;
+    constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
+    constexpr bool kLockstep = KernelShape<Rhs, DENSE>::kLockstep;
     const long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
     const bool in_range = q < A.npts;
     bool active = in_range;
@@ -59,27 +77,24 @@ __global__ void __launch_bounds__(kBlock) flowmap_kernel(const __grid_constant__
     const long long row_len = DENSE ? (long long)A.n_out * N : N;
     double *row = A.out + q * row_len;
 
-    if (active) {
-        const Rhs rhs(A.rhs);
-        if (DENSE) {
-            RowSink<N> sink{row, A.out_aligned16 != 0};
+    const Rhs rhs(A.rhs);
+    const bool integrate = active && (A.xend != A.x0);   // T == 0: the flow map is the identity
+    if (DENSE) {
+        RowSink<N> sink{row, A.out_aligned16 != 0};
+        if (active) {
             sink(0, y);  // row 0 is the initial condition
-            if (A.xend == A.x0) {
-                status = B200CS_ST_OK;
+            if (!integrate)
                 for (int k = 1; k < A.n_out; ++k) sink(k, y);
-            } else {
-                status = dop853_integrate<true>(rhs, y, A.x0, A.xend, A.rtol, A.atol, A.n_out, A.out_p0,
-                                                A.out_t0, A.out_step, sink, cnt);
-            }
-        } else {
-            status = (A.xend == A.x0)
-                         ? B200CS_ST_OK
-                         : dop853_integrate<false>(rhs, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0, 0.0,
-                                                   NoSink<N>{}, cnt);
+        } else if (in_range) {
+            for (long long k = 0; k < row_len; ++k) row[k] = 0.0;  // masked: zeros (integration.py:163, 515)
         }
-    } else if (in_range && DENSE) {
-        for (long long k = 0; k < row_len; ++k) row[k] = 0.0;  // masked: zeros (integration.py:163, 515)
+        status = dop853_integrate<true, kLockstep>(rhs, integrate, y, A.x0, A.xend, A.rtol, A.atol, A.n_out,
+                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt);
+    } else {
+        status = dop853_integrate<false, kLockstep>(rhs, integrate, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0,
+                                                    0.0, NoSink<N>{}, cnt);
     }
+    if (active && !integrate) status = B200CS_ST_OK;
 
     if (in_range) {
         if (!DENSE) {
@@ -115,21 +130,26 @@ __global__ void __launch_bounds__(kBlock) flowmap_kernel(const __grid_constant__
     }
 }
 
-template <class Rhs>
-void launch_rhs(const IntegArgs &A, bool grid_mode, cudaStream_t s) {
+template <class Rhs, bool DENSE, bool GRID>
+void launch_one(const IntegArgs &A, cudaStream_t s) {
+    constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
     const long long blocks = (A.npts + kBlock - 1) / kBlock;
     if (blocks <= 0) return;
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
-    const dim3 g((unsigned)blocks), b(kBlock);
+    flowmap_kernel<Rhs, DENSE, GRID><<<(unsigned)blocks, kBlock, 0, s>>>(A);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+template <class Rhs>
+void launch_rhs(const IntegArgs &A, bool grid_mode, cudaStream_t s) {
     const bool dense = A.n_out >= 2;
     if (dense) {
-        if (grid_mode) flowmap_kernel<Rhs, true, true><<<g, b, 0, s>>>(A);
-        else flowmap_kernel<Rhs, true, false><<<g, b, 0, s>>>(A);
+        if (grid_mode) launch_one<Rhs, true, true>(A, s);
+        else launch_one<Rhs, true, false>(A, s);
     } else {
-        if (grid_mode) flowmap_kernel<Rhs, false, true><<<g, b, 0, s>>>(A);
-        else flowmap_kernel<Rhs, false, false><<<g, b, 0, s>>>(A);
+        if (grid_mode) launch_one<Rhs, false, true>(A, s);
+        else launch_one<Rhs, false, false>(A, s);
     }
-    B2_CHECK_CUDA(cudaGetLastError());
 }
 
 }  // namespace

@@ -38,13 +38,16 @@ struct DoubleGyre {
     const RhsParams &P;
     __device__ __forceinline__ explicit DoubleGyre(const RhsParams &P_) : P(P_) {}
 
-    // a(t) = eps * sin(omega*tt + psi), tt = p0*t   (flows.py:1152-1153)
+    // a(t) = eps * sin(omega*tt + psi), tt = p0*t   (flows.py:1152-1153).
+    // p[0] is the integration direction, +-1 (userguide.rst:217-227), so folding it into omega
+    // (and into the amplitudes below) is an exact sign change, not a rounding.
     template <int M>
     __device__ __forceinline__ void time_part(const double (&t)[M], double (&aux)[M]) const {
-        const double p0 = P.p[0], eps = P.p[2], omega = P.p[4], psi = P.p[5];
+        const double eps = P.p[2], psi = P.p[5];
+        const double omega_p0 = P.p[4] * P.p[0];
         double arg[M], sa[M];
 #pragma unroll
-        for (int m = 0; m < M; ++m) arg[m] = fma(omega, p0 * t[m], psi);
+        for (int m = 0; m < M; ++m) arg[m] = fma(omega_p0, t[m], psi);
         sin_v<M>(arg, sa);
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = eps * sa[m];
@@ -59,16 +62,21 @@ struct DoubleGyre {
     // differences), both forms vanish exactly on the walls x = 0 and y = 0, and the parity tests
     // (step-count equality, 1e-8 x domain) are the guard.
     __device__ __forceinline__ void eval(double a, double /*t*/, const double (&y)[2], double (&dy)[2]) const {
-        const double p0 = P.p[0], A = P.p[1], alpha = P.p[3];
-        const double hpiA = 0.5 * (kPi * A);  // exact scaling of pi*A
+        const double c = (0.5 * (kPi * P.p[1])) * P.p[0];  // p0 * pi*A/2 (exact scalings of pi*A)
+        const double damp = -(P.p[3] * P.p[0]);            // -p0*alpha, 0 for the default flow
         const double b = 1.0 - 2.0 * a;
         const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
         const double df = fma(2.0 * a, y[0], b);
         const double arg[2] = {kPi * (f + y[1]), kPi * (f - y[1])};
         double s[2];
         sin_v<2>(arg, s);
-        dy[0] = p0 * fma(-hpiA, s[0] + s[1], -(alpha * y[0]));
-        dy[1] = p0 * fma(hpiA * (s[0] - s[1]), df, -(alpha * y[1]));
+        if (damp != 0.0) {
+            dy[0] = fma(-c, s[0] + s[1], damp * y[0]);
+            dy[1] = fma(c * (s[0] - s[1]), df, damp * y[1]);
+        } else {
+            dy[0] = -c * (s[0] + s[1]);
+            dy[1] = (c * (s[0] - s[1])) * df;
+        }
     }
 };
 
