@@ -175,6 +175,20 @@ B200CS_API int b200cs_lavd_grid_2d(const double *flowmap_n /*[nx,ny,n,2]*/, int6
                         const double *yrav, int64_t nrav, double period_x, double period_y,
                         const uint8_t *mask, double *vort_avg, int vort_avg_in,
                         double *lavd /*[nx,ny]*/, void *stream);
+/* flowmap_n_grid_2D + lavd_grid_2D fused ("LAVD carried along the trajectories"): the n-time
+ * trajectory array [nx,ny,n,2] (10 GB at 1024^2 x 601) is never materialised -- the integration
+ * kernel's dense-output sink evaluates |vort - vort_avg[k]| as each output time is produced and
+ * accumulates the composite Simpson sum.  vort_avg (nullable [n]): precomputed spatial means;
+ * when NULL they are computed over the (x, y) grid itself (diagnostics.py:324-331 with
+ * xrav, yrav = meshgrid(x, y).ravel()).  flowmap_out (nullable [nx,ny,2]) receives the final
+ * positions, tspan (nullable [n]) the output times params[0]*t_eval. */
+B200CS_API int b200cs_lavd_flowmap_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
+                                const double *y, int64_t ny, const double *params, int nparams,
+                                int method, double rtol, double atol, const uint8_t *mask, int n,
+                                int vort, double period_x, double period_y, const double *vort_avg,
+                                double *lavd, double *flowmap_out, double *tspan, int32_t *status,
+                                int64_t *stats, void *stream);
+
 /* partial sums for the spatial mean: sums[k] = sum_q vort(tspan[k], xrav[q], yrav[q]) */
 B200CS_API int b200cs_lavd_vort_sums(int vort, const double *tspan, int64_t n, const double *xrav,
                           const double *yrav, int64_t nrav, double *sums /*[n]*/, void *stream);

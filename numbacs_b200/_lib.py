@@ -42,6 +42,8 @@ PROTOTYPES = {
                                     _d, _d, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "b200cs_lavd_grid_2d": [_vp, _i64, _i64, _i64, _vp, _i, _vp, _vp, _i64, _d, _d, _vp, _vp, _i,
                             _vp, _vp],
+    "b200cs_lavd_flowmap_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp, _i, _i, _d, _d,
+                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200cs_lavd_vort_sums": [_i, _vp, _i64, _vp, _vp, _i64, _vp, _vp],
     "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
 }

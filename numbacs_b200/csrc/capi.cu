@@ -468,7 +468,7 @@ int b200cs_lavd_vort_sums(int vort, const double *tspan, int64_t n, const double
         cudaStream_t s = static_cast<cudaStream_t>(stream);
         In<double> dts(tspan, n, s), dxr(xrav, nrav, s), dyr(yrav, nrav, s);
         Out<double> dsum(sums, n, s);
-        launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, dsum.dev, s);
+        launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, 0, dsum.dev, s);
         dsum.download();
         if (dsum.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
     });
@@ -502,7 +502,7 @@ int b200cs_lavd_grid_2d(const double *flowmap_n, int64_t nx, int64_t ny, int64_t
         }
         if (!vort_avg_in) {
             In<double> dxr(xrav, nrav, s), dyr(yrav, nrav, s);
-            launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, avg_dev, s);
+            launch_vort_sums(*f, dts.dev, n, dxr.dev, dyr.dev, nrav, 0, avg_dev, s);
             launch_div_scalar(avg_dev, n, (double)nrav, s);  // np.mean
         }
         launch_lavd(*f, dfm.dev, (long long)np, n, dts.dev, avg_dev, period_x, period_y, dmask.dev,
@@ -510,6 +510,87 @@ int b200cs_lavd_grid_2d(const double *flowmap_n, int64_t nx, int64_t ny, int64_t
         dlavd.download();
         if (!vort_avg_in) davg.download();
         if (dlavd.staged() || davg.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_lavd_flowmap_grid_2d(int flow, double t0, double T, const double *x, int64_t nx, const double *y,
+                                int64_t ny, const double *params, int nparams, int method, double rtol,
+                                double atol, const uint8_t *mask, int n, int vort, double period_x,
+                                double period_y, const double *vort_avg, double *lavd, double *flowmap_out,
+                                double *tspan, int32_t *status, int64_t *stats, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(method == B200CS_METHOD_DOP853, "only method='dop853' is implemented on the GPU");
+        B2_REQUIRE(n >= 3, "lavd needs at least 3 output times (got %d)", n);
+        B2_REQUIRE(rtol > 0.0 && atol >= 0.0, "rtol must be > 0 and atol >= 0");
+        B2_REQUIRE(x && y && lavd && nx >= 0 && ny >= 0, "bad argument");
+        auto f = registry_get(flow);
+        B2_REQUIRE(f->kind >= 0 && f->ndim == 2, "handle %d is not a 2-D flow", flow);
+        auto fv = registry_get(vort);
+        B2_REQUIRE(fv->kind == -1, "handle %d is a flow, not a scalar field", vort);
+        check_device(*f);
+        check_device(*fv);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const long long npts = (long long)nx * ny;
+
+        IntegArgs A{};
+        read_params(params, nparams, f->min_params, A.rhs);
+        fill_rhs(*f, A.rhs);
+        const double p0 = A.rhs.p[0];
+        A.x0 = p0 * t0;
+        A.xend = p0 * (t0 + T);
+        A.rtol = rtol;
+        A.atol = atol;
+        A.n_out = n;
+        A.out_p0 = p0;
+        A.out_t0 = t0;
+        A.out_step = ((t0 + T) - t0) / (double)(n - 1);
+        A.nx = nx;
+        A.ny = ny;
+        A.npts = npts;
+        std::vector<double> ts(n);  // physical output times params[0]*t_eval (integration.py:533)
+        for (int k = 0; k < n; ++k)
+            ts[k] = p0 * ((k == n - 1) ? p0 * (t0 + T) : p0 * (t0 + (double)k * A.out_step));
+        if (tspan) {
+            if (is_device_ptr(tspan)) B2_CHECK_CUDA(cudaMemcpy(tspan, ts.data(), sizeof(double) * n, cudaMemcpyHostToDevice));
+            else std::memcpy(tspan, ts.data(), sizeof(double) * n);
+        }
+        if (npts == 0) return;
+        Scratch ts_dev(sizeof(double) * n, s), avg_dev(sizeof(double) * n, s);
+        B2_CHECK_CUDA(cudaMemcpyAsync(ts_dev.ptr, ts.data(), sizeof(double) * n, cudaMemcpyHostToDevice, s));
+        B2_CHECK_CUDA(cudaStreamSynchronize(s));  // ts is a local
+        In<double> dx(x, nx, s), dy(y, ny, s);
+        In<uint8_t> dmask(mask, npts, s);
+        if (vort_avg) {
+            B2_CHECK_CUDA(cudaMemcpyAsync(avg_dev.ptr, vort_avg, sizeof(double) * n, cudaMemcpyDefault, s));
+        } else {
+            launch_vort_sums(*fv, static_cast<double *>(ts_dev.ptr), n, dx.dev, dy.dev, npts, ny,
+                             static_cast<double *>(avg_dev.ptr), s);
+            launch_div_scalar(static_cast<double *>(avg_dev.ptr), n, (double)npts, s);  // np.mean
+        }
+        Out<double> dlavd(lavd, npts, s);
+        Out<double> dfm(flowmap_out, (size_t)npts * 2, s);
+        Out<int32_t> dstatus(status, npts, s);
+        Out<int64_t> dstats(stats, 3, s, /*upload_first=*/true);
+        A.x = dx.dev;
+        A.y = dy.dev;
+        A.mask = dmask.dev;
+        A.out = dfm.dev;
+        A.status = dstatus.dev;
+        A.stats = reinterpret_cast<unsigned long long *>(dstats.dev);
+        A.vort = make_scalar_dev(*fv);
+        A.tspan_phys = static_cast<const double *>(ts_dev.ptr);
+        A.vort_avg = static_cast<const double *>(avg_dev.ptr);
+        A.period_x = period_x;
+        A.period_y = period_y;
+        A.lavd = dlavd.dev;
+        launch_lavd_flowmap(*f, A, s);
+        dlavd.download();
+        dfm.download();
+        dstatus.download();
+        dstats.download();
+        if (dlavd.staged() || dfm.staged() || dstatus.staged() || dstats.staged())
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

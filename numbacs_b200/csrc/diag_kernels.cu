@@ -30,21 +30,6 @@ SplineGridDev make_grid_dev(const FlowSpec &f) {
 
 namespace {
 
-struct ScalarDev {
-    SplineGridDev g;
-    const double *C;
-    int linear;
-};
-
-__device__ __forceinline__ double scalar_at(const ScalarDev &S, double t, double x, double y) {
-    return S.linear ? eval_linear_s(S.g, S.C, t, x, y) : eval_spline_s(S.g, S.C, t, x, y);
-}
-
-__device__ __forceinline__ double pymod_any(double a, double m) {
-    double r = fmod(a, m);
-    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
-    return r;
-}
 
 __global__ void scalar_eval_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ pts,
                                    long long npts, double *__restrict__ out) {
@@ -59,14 +44,15 @@ constexpr int kRedThreads = 256;
 __global__ void __launch_bounds__(kRedThreads)
 vort_partial_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ tspan,
                     const double *__restrict__ xr, const double *__restrict__ yr, long long nrav,
-                    double *__restrict__ partial) {
+                    long long ny_grid, double *__restrict__ partial) {
     __shared__ double red[kRedThreads / 32];
     const int k = blockIdx.y;
     const double t = tspan[k];
     double acc = 0.0;
     for (long long q = (long long)blockIdx.x * kRedThreads + threadIdx.x; q < nrav;
          q += (long long)gridDim.x * kRedThreads)
-        acc += scalar_at(S, t, xr[q], yr[q]);
+        // ny_grid > 0: (xr, yr) are the 1-D axes of an 'ij' grid; else the raveled meshgrid
+        acc += (ny_grid > 0) ? scalar_at(S, t, xr[q / ny_grid], yr[q % ny_grid]) : scalar_at(S, t, xr[q], yr[q]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -214,14 +200,6 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(int iters, double seed, 
     if (s == 123.456) sink[0] = s;  // never true: keeps the chains alive
 }
 
-ScalarDev make_scalar_dev(const FlowSpec &f) {
-    ScalarDev S{};
-    S.g = make_grid_dev(f);
-    S.C = static_cast<const double *>(f.coef);
-    S.linear = f.linear;
-    return S;
-}
-
 void init_thomas_table() {
     // per-device upload: constant memory is per context/device, so redo it per device
     static std::mutex mu;
@@ -240,6 +218,14 @@ void init_thomas_table() {
 
 }  // namespace
 
+ScalarDev make_scalar_dev(const FlowSpec &f) {
+    ScalarDev S{};
+    S.g = make_grid_dev(f);
+    S.C = static_cast<const double *>(f.coef);
+    S.linear = f.linear;
+    return S;
+}
+
 void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s) {
     if (npts <= 0) return;
     const ScalarDev S = make_scalar_dev(f);
@@ -248,7 +234,7 @@ void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, do
 }
 
 void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
-                      const double *yr, long long nrav, double *sums, cudaStream_t s) {
+                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s) {
     if (n <= 0) return;
     B2_REQUIRE(n <= 65535, "too many output times for the LAVD mean (%lld)", n);
     const ScalarDev S = make_scalar_dev(f);
@@ -257,7 +243,7 @@ void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const
     if (nb < 1) nb = 1;
     Scratch partial(sizeof(double) * n * nb, s);
     vort_partial_kernel<<<dim3((unsigned)nb, (unsigned)n), kRedThreads, 0, s>>>(
-        S, tspan, xr, yr, nrav, static_cast<double *>(partial.ptr));
+        S, tspan, xr, yr, nrav, ny_grid, static_cast<double *>(partial.ptr));
     B2_CHECK_CUDA(cudaGetLastError());
     vort_final_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(static_cast<double *>(partial.ptr),
                                                                  (int)nb, n, sums);

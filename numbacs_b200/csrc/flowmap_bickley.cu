@@ -5,4 +5,6 @@ namespace b200cs {
 
 void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s) { launch_rhs<BickleyJet>(A, grid_mode, s); }
 
+void launch_lavd_bickley(const IntegArgs &A, cudaStream_t s) { launch_lavd_one<BickleyJet>(A, s); }
+
 }  // namespace b200cs

@@ -9,6 +9,20 @@ void launch_flowmap_dg(const IntegArgs &A, bool grid_mode, cudaStream_t s);
 void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s);
 void launch_flowmap_abc(const IntegArgs &A, bool grid_mode, cudaStream_t s);
 void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_lavd_dg(const IntegArgs &A, cudaStream_t s);
+void launch_lavd_bickley(const IntegArgs &A, cudaStream_t s);
+void launch_lavd_spline(int spherical, const IntegArgs &A, cudaStream_t s);
+
+void launch_lavd_flowmap(const FlowSpec &f, const IntegArgs &A, cudaStream_t s) {
+    switch (f.kind) {
+    case B200CS_FLOW_DOUBLE_GYRE: launch_lavd_dg(A, s); break;
+    case B200CS_FLOW_BICKLEY_JET: launch_lavd_bickley(A, s); break;
+    case B200CS_FLOW_SPLINE2D: launch_lavd_spline(f.spherical, A, s); break;
+    default:
+        set_error("LAVD needs a 2-D flow (kind %d)", f.kind);
+        throw Fail{B200CS_E_INVALID};
+    }
+}
 
 void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s) {
     switch (f.kind) {

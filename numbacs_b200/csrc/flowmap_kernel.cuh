@@ -16,7 +16,10 @@ namespace b200cs {
 
 namespace {
 
-// Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow.
+// Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow
+// (measured best for the Bickley jet, whose particles need 7-50 attempts: big lockstep blocks wait
+// for their slowest particle).  The spline kernels gain 32 % from lockstep (their 64-tap RHS makes
+// the unrolled body even larger).
 // The final-time double-gyre kernel (the headline workload) runs ONE 640-thread block per SM
 // (20 warps at <= 96 registers) with a block barrier before every step attempt: all 20 warps walk
 // the 62 KB unrolled body together, which removes most of its instruction-cache misses.
@@ -29,6 +32,12 @@ struct KernelShape {
 template <>
 struct KernelShape<DoubleGyre, false> {
     static constexpr int kThreads = 640;
+    static constexpr int kMinBlocks = 1;
+    static constexpr bool kLockstep = true;
+};
+template <int SPH>
+struct KernelShape<Spline2D<SPH>, false> {
+    static constexpr int kThreads = 448;   // <= 146 registers
     static constexpr int kMinBlocks = 1;
     static constexpr bool kLockstep = true;
 };
@@ -128,6 +137,91 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
             atomicAdd(&A.stats[2], rej);
         }
     }
+}
+
+// ---- K1n + K3 fused: LAVD carried along the trajectory ------------------------------------------
+// Replaces flowmap_n_grid_2D followed by lavd_grid_2D's particle loop
+// (integration.py:467-533, diagnostics.py:336-377; Simpson rule utils.py:611-655) without ever
+// materialising the [nx, ny, n, 2] trajectory array (10 GB at config 4): the dense-output sink
+// evaluates |vort(t_k, traj(t_k)) - vort_avg[k]| as row k is produced and accumulates the composite
+// Simpson sum on the fly (the three last integrand values are kept for the odd-interval rule).
+struct LavdSink {
+    const ScalarDev *S;
+    const double *tspan, *vavg;
+    double px, py;
+    int n;             // number of output times
+    int m_simpson;     // number of intervals covered by the 1/3 rule: n-1 if even, n-2 if odd
+    double f0, sum, fl1, fl2, fl3;  // first value, weighted interior sum, last three values
+    __device__ __forceinline__ void operator()(int k, const double (&v)[2]) {
+        double x = v[0], y = v[1];
+        if (px != 0.0) x = pymod_any(x, px);
+        if (py != 0.0) y = pymod_any(y, py);
+        const double f = fabs(scalar_at(*S, __ldg(tspan + k), x, y) - __ldg(vavg + k));
+        fl3 = fl2;
+        fl2 = fl1;
+        fl1 = f;
+        if (k == 0) f0 = f;
+        else if (k < m_simpson) sum = fma((k & 1) ? 4.0 : 2.0, f, sum);
+    }
+    // composite Simpson (utils.py:611-655) with spacing h
+    __device__ __forceinline__ double finish(double h) const {
+        const int m = n - 1;
+        if ((m & 1) == 0) return (f0 + fl1 + sum) * (h / 3.0);
+        double val = (f0 + fl2 + sum) * (h / 3.0);
+        val += (5.0 * h / 12.0) * fl1 + (2.0 * h / 3.0) * fl2 - (h / 12.0) * fl3;
+        return val;
+    }
+};
+
+template <class Rhs>
+__global__ void __launch_bounds__(128) lavd_flowmap_kernel(const __grid_constant__ IntegArgs A) {
+    static_assert(Rhs::N == 2, "LAVD is defined for 2-D flows");
+    const long long q = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (q >= A.npts) return;
+    const bool active = (A.mask == nullptr || A.mask[q] == 0);
+    double y[2] = {0.0, 0.0};
+    StepCounts cnt;
+    int status = B200CS_ST_MASKED;
+    double lavd = 0.0;
+    if (active) {
+        const long long i = q / A.ny, j = q - i * A.ny;
+        y[0] = A.x[i];
+        y[1] = A.y[j];
+        const int m = A.n_out - 1;
+        LavdSink sink{&A.vort, A.tspan_phys, A.vort_avg, A.period_x, A.period_y, A.n_out,
+                      (m & 1) ? m - 1 : m, 0.0, 0.0, 0.0, 0.0, 0.0};
+        sink(0, y);
+        const Rhs rhs(A.rhs);
+        if (A.xend == A.x0) {
+            status = B200CS_ST_OK;
+            for (int k = 1; k < A.n_out; ++k) sink(k, y);
+        } else {
+            status = dop853_integrate<true, false>(rhs, true, y, A.x0, A.xend, A.rtol, A.atol, A.n_out,
+                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt);
+        }
+        lavd = sink.finish(fabs(A.tspan_phys[1] - A.tspan_phys[0]));
+    }
+    A.lavd[q] = lavd;
+    if (A.out) {  // optional final positions
+        A.out[2 * q] = y[0];
+        A.out[2 * q + 1] = y[1];
+    }
+    if (A.status) A.status[q] = status;
+    if (A.stats && active) {
+        const int nstep = cnt.accepted + cnt.rejected;
+        atomicAdd(&A.stats[0], 2ull + 11ull * nstep + cnt.accepted + 3ull * cnt.dense);
+        atomicAdd(&A.stats[1], (unsigned long long)cnt.accepted);
+        atomicAdd(&A.stats[2], (unsigned long long)cnt.rejected);
+    }
+}
+
+template <class Rhs>
+void launch_lavd_one(const IntegArgs &A, cudaStream_t s) {
+    const long long blocks = (A.npts + 127) / 128;
+    if (blocks <= 0) return;
+    B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
+    lavd_flowmap_kernel<Rhs><<<(unsigned)blocks, 128, 0, s>>>(A);
+    B2_CHECK_CUDA(cudaGetLastError());
 }
 
 template <class Rhs, bool DENSE, bool GRID>

@@ -9,4 +9,10 @@ void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cu
     else launch_rhs<Spline2D<0>>(A, grid_mode, s);
 }
 
+void launch_lavd_spline(int spherical, const IntegArgs &A, cudaStream_t s) {
+    if (spherical == 1) launch_lavd_one<Spline2D<1>>(A, s);
+    else if (spherical == 2) launch_lavd_one<Spline2D<2>>(A, s);
+    else launch_lavd_one<Spline2D<0>>(A, s);
+}
+
 }  // namespace b200cs

@@ -25,6 +25,13 @@ struct IntegArgs {
     int *status;
     int *steps;
     unsigned long long *stats;
+    // fused LAVD (lavd_flowmap kernels only): |vort(traj) - vort_avg| integrated by composite
+    // Simpson while the trajectory is being produced, so the [nx,ny,n,2] array never exists
+    ScalarDev vort;
+    const double *tspan_phys;  // [n_out] physical output times params[0]*t_eval
+    const double *vort_avg;    // [n_out] spatial means
+    double period_x, period_y;
+    double *lavd;              // [npts]
 };
 
 void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s);
@@ -41,7 +48,9 @@ SplineGridDev make_grid_dev(const FlowSpec &f);
 
 void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s);
 void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
-                      const double *yr, long long nrav, double *sums, cudaStream_t s);
+                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s);
+ScalarDev make_scalar_dev(const FlowSpec &f);
+void launch_lavd_flowmap(const FlowSpec &f, const IntegArgs &A, cudaStream_t s);
 void launch_lavd(const FlowSpec &f, const double *fm_n, long long npts, long long n, const double *tspan,
                  const double *vavg, double period_x, double period_y, const uint8_t *mask, double *lavd,
                  cudaStream_t s);

@@ -163,4 +163,22 @@ __device__ __forceinline__ double eval_linear_s(const SplineGridDev &g, const do
     return v;
 }
 
+// a scalar field (vorticity): cubic-spline coefficients or the raw field for trilinear evaluation
+struct ScalarDev {
+    SplineGridDev g;
+    const double *C;
+    int linear;
+};
+
+__device__ __forceinline__ double scalar_at(const ScalarDev &S, double t, double x, double y) {
+    return S.linear ? eval_linear_s(S.g, S.C, t, x, y) : eval_spline_s(S.g, S.C, t, x, y);
+}
+
+// Python float modulo (result takes the sign of the divisor), diagnostics.py:350-376
+__device__ __forceinline__ double pymod_any(double a, double m) {
+    double r = fmod(a, m);
+    if (r != 0.0 && ((r < 0.0) != (m < 0.0))) r += m;
+    return r;
+}
+
 }  // namespace b200cs

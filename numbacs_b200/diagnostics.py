@@ -13,7 +13,8 @@ from . import _lib
 from .flows import ScalarField
 from .integration import _info_bufs, _fill_info, _method
 
-__all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D"]
+__all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D",
+           "lavd_flowmap_grid_2D"]
 
 
 def ftle_grid_2D(flowmap, T, dx, dy, mask=None, *, device_out=False):
@@ -93,3 +94,30 @@ def lavd_grid_2D(flowmap_n, tspan, T, vort_interp, xrav, yrav, period_x=0.0, per
         fm.ptr, nx, ny, n, ts.ptr, vort_interp.handle, xr.ptr, yr.ptr, nrav, float(period_x),
         float(period_y), ma.ptr, va_ptr, va_in, out.ptr, _lib.current_stream(dev)))
     return out.obj
+
+
+def lavd_flowmap_grid_2D(funcptr, t0, T, x, y, params, vort_interp, n=50, method="dop853", rtol=1e-6,
+                         atol=1e-8, period_x=0.0, period_y=0.0, mask=None, *, vort_avg=None,
+                         return_flowmap=False, device_out=False, info=None):
+    """flowmap_n_grid_2D + lavd_grid_2D fused: the LAVD is accumulated along each trajectory while
+    it is integrated, so the (nx, ny, n, 2) array is never stored.  Returns (lavd, tspan) or
+    (lavd, tspan, final_flowmap).  Same result as the two reference calls
+    (integration.py:467-533, diagnostics.py:272-379) up to the order of the Simpson summation."""
+    if not isinstance(vort_interp, ScalarField):
+        raise NotImplementedError("vort_interp must come from numbacs_b200.flows.get_callable_scalar(_linear)")
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
+    nx, ny = int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    dev = bool(device_out or xa.on_device or ya.on_device)
+    lavd = _lib.alloc_out((nx, ny), np.float64, dev)
+    fm = _lib.alloc_out((nx, ny, 2), np.float64, dev) if return_flowmap else _lib.Arg(None, None, False)
+    tspan = np.empty(int(n), np.float64)
+    status, _, stats = _info_bufs(info, (nx, ny), dev)
+    va = _lib.arg_in(vort_avg) if vort_avg is not None else _lib.Arg(None, None, False)
+    _lib.check(_lib.load().b200cs_lavd_flowmap_grid_2d(
+        int(funcptr), float(t0), float(T), xa.ptr, nx, ya.ptr, ny, pa.ptr, int(pa.obj.shape[0]),
+        _method(method), float(rtol), float(atol), ma.ptr, int(n), vort_interp.handle, float(period_x),
+        float(period_y), va.ptr, lavd.ptr, fm.ptr, C.c_void_p(tspan.ctypes.data), status.ptr, stats.ptr,
+        _lib.current_stream(dev)))
+    if info is not None:
+        info["status"], info["stats"] = status.obj, stats.obj
+    return (lavd.obj, tspan, fm.obj) if return_flowmap else (lavd.obj, tspan)

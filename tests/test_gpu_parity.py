@@ -416,6 +416,20 @@ def test_lavd_cubic_spline(nb, oracle):
             assert np.abs(got - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
     with pytest.raises(NotImplementedError):
         nb.diagnostics.lavd_grid_2D(fmn, ts, 6.0, lambda p: p, Xg.ravel(), Yg.ravel())
+    # fused path: LAVD accumulated along the trajectories inside the integration kernel
+    fo = oracle.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")
+    for n in (12, 13):
+        for px, py in ((0.0, 0.0), (1.5, 0.7)):
+            got, ts, fm_end = nb.diagnostics.lavd_flowmap_grid_2D(f, 1.0, 6.0, xg, yg, np.array([1.0]), w, n=n,
+                                                                  period_x=px, period_y=py, mask=mask,
+                                                                  return_flowmap=True)
+            fmno, tso = oracle.flowmap_n_grid_2D(fo, 1.0, 6.0, xg, yg, np.array([1.0]), n=n)
+            ref = oracle.lavd_grid_2D(fmno, tso, 6.0, wo, Xg.ravel(), Yg.ravel(), px, py, mask=mask)
+            assert np.array_equal(ts, tso)
+            assert np.array_equal(got == 0.0, ref == 0.0)
+            # trajectories agree to ~1e-9 (spline flow), so does the integral
+            assert np.abs(got - ref).max() <= 1e-7 * max(1.0, np.abs(ref).max())
+            assert np.abs(fm_end[~mask] - fmno[:, :, -1][~mask]).max() <= 1e-7
 
 
 # ------------------------------------------------------------------ API behaviour / edge cases
