@@ -262,12 +262,17 @@ def run_b200(args):
         dist.barrier()
     clocks = sampler.stop() if sampler else None
 
-    # ---- end-to-end region: host buffers in, host FTLE block out, every step
+    # ---- end-to-end region: ONE C-ABI call per step with HOST buffers only -- x / y slab in from
+    # pinned memory, the FTLE block out to pinned memory (b200cs_flowmap_ftle_grid_2d integrates in
+    # row chunks and streams finished FTLE rows over PCIe while the next chunk is integrated).
+    # Multi-GPU: every rank passes its row block plus one stencil-only halo row per interior edge
+    # (recomputed, 2 of nx/N rows), so the end-to-end path needs no exchange at all.
+    xs_host = x_host[i0 - has_lo:i1 + has_hi]
     def e2e_step():
-        xr = x_host[i0:i1].to("cuda", non_blocking=True)
-        yv = y_host.to("cuda", non_blocking=True)
-        step(xr, yv)
-        ftle_host.copy_(ftle, non_blocking=True)
+        _lib.check(L.b200cs_flowmap_ftle_grid_2d(
+            f, T0, TINT, C.c_void_p(xs_host.data_ptr()), xs_host.shape[0], C.c_void_p(y_host.data_ptr()), n,
+            C.c_void_p(p_arr.ctypes.data), len(p_arr), 0, RTOL, ATOL, None, dx, dy, has_lo, has_hi,
+            None, C.c_void_p(ftle_host.data_ptr()), None, None, sptr))
 
     e2e_step()
     sync_all()
@@ -332,10 +337,12 @@ def run_b200(args):
                        "l2": "no flush: every step rewrites 24 B/point of outputs "
                              f"({24 * pts / world / 1e9:.2f} GB per GPU >> 126 MB L2), inputs are 2 x {n} doubles"},
             "e2e": {"value": e2e_val, "unit": "grid points/s",
-                    "h2d_bytes_per_step": int(8 * (n + n * world)),
+                    "h2d_bytes_per_step": int(8 * (n + 2 * (world - 1) + n * world)),
                     "d2h_bytes_per_step": int(8 * pts), "ms_per_step": e2e_ms / K,
-                    "result": "FTLE field copied to pinned host memory every step; flow map stays in HBM"},
-            "gpu_launches": 2 * K * world,
+                    "result": "one b200cs_flowmap_ftle_grid_2d call per rank and step, host pointers only: x/y "
+                              "from pinned memory, FTLE field to pinned memory (downloads overlap the "
+                              "integration of later row chunks); the flow map stays in HBM"},
+            "gpu_launches": 2 * K * world,  # timed (device) region: flow-map + FTLE kernel per step and rank
             "roofline": {"bound": "fp64", "achieved": fm_tflops_per_gpu, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": fm_tflops_per_gpu / fp64_peak, "traffic": traffic,
                          "kernel": "flowmap_kernel<DoubleGyre>", "kernel_ms": fm_ms,

@@ -63,6 +63,24 @@ static void require_device() {
                   e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
         throw Fail{B200CS_E_CUDA};
     }
+    // Scratch buffers come from the stream-ordered allocator; keep freed blocks cached in the pool
+    // (the default threshold of 0 hands multi-GB staging buffers back to the driver at every
+    // synchronisation and re-maps them on the next call).
+    static std::mutex mu;
+    static bool tuned[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!tuned[dev]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long keep = ~0ull;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            cudaGetLastError();
+            tuned[dev] = true;
+        }
+    }
 }
 
 static void read_grid9(const double *grid9, Axis3 &g) {
@@ -445,6 +463,68 @@ int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, 
             fm_host_copy = flowmap_out != nullptr;
         }
         In<uint8_t> dmask(mask, np, s);  // staged once, used by both kernels
+        const bool host_ftle = !is_device_ptr(ftle_out);
+        constexpr long long kChunkRows = 1024;
+        if ((host_ftle || fm_host_copy) && nx >= 2 * kChunkRows && np >= (size_t(1) << 22)) {
+            // Host outputs on a large grid: pipeline.  Rows are integrated in chunks; as soon as a
+            // chunk's successor has been integrated its FTLE rows are complete and go out over
+            // PCIe on a second stream while the next chunk is being integrated (the integration
+            // is compute-bound, the download is free).
+            In<double> dxs(x, nx, s), dys(y, ny, s);
+            Out<int32_t> dstatus(status, np, s);
+            Out<int64_t> dstats(stats, 3, s, /*upload_first=*/true);
+            Scratch ftle_tmp;
+            double *ftle_dev = ftle_out;
+            if (host_ftle) {
+                ftle_tmp = Scratch((size_t)rows_out * ny * sizeof(double), s);
+                ftle_dev = static_cast<double *>(ftle_tmp.ptr);
+            }
+            cudaStream_t s2 = nullptr;
+            B2_CHECK_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            std::vector<cudaEvent_t> events;
+            long long ftle_done = halo_lo, fm_done = 0;
+            try {
+                for (long long c0 = 0; c0 < nx; c0 += kChunkRows) {
+                    const long long c1 = (c0 + kChunkRows < nx) ? c0 + kChunkRows : nx;
+                    run_flowmap(flow, t0, T, true, dxs.dev + c0, c1 - c0, dys.dev, ny, nullptr, 0, 2, params,
+                                nparams, method, rtol, atol, dmask.dev ? dmask.dev + c0 * ny : nullptr, 0,
+                                fm_dev + c0 * ny * 2, nullptr, dstatus.dev ? dstatus.dev + c0 * ny : nullptr,
+                                nullptr, dstats.dev, s);
+                    const long long hi = (c1 == nx) ? (long long)nx - halo_hi : c1 - 1;  // stencil complete below hi
+                    if (hi > ftle_done)
+                        launch_ftle(fm_dev, nx, ny, T, dx, dy, dmask.dev, ftle_dev + (ftle_done - halo_lo) * ny,
+                                    ftle_done, hi, halo_lo == 0, halo_hi == 0, s);
+                    cudaEvent_t ev;
+                    B2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    events.push_back(ev);
+                    B2_CHECK_CUDA(cudaEventRecord(ev, s));
+                    B2_CHECK_CUDA(cudaStreamWaitEvent(s2, ev, 0));
+                    if (host_ftle && hi > ftle_done)
+                        B2_CHECK_CUDA(cudaMemcpyAsync(ftle_out + (ftle_done - halo_lo) * ny,
+                                                      ftle_dev + (ftle_done - halo_lo) * ny,
+                                                      (size_t)(hi - ftle_done) * ny * sizeof(double),
+                                                      cudaMemcpyDeviceToHost, s2));
+                    if (fm_host_copy)
+                        B2_CHECK_CUDA(cudaMemcpyAsync(flowmap_out + fm_done * ny * 2, fm_dev + fm_done * ny * 2,
+                                                      (size_t)(c1 - fm_done) * ny * 2 * sizeof(double),
+                                                      cudaMemcpyDeviceToHost, s2));
+                    if (hi > ftle_done) ftle_done = hi;
+                    fm_done = c1;
+                }
+                dstatus.download();
+                dstats.download();
+                B2_CHECK_CUDA(cudaStreamSynchronize(s2));
+                B2_CHECK_CUDA(cudaStreamSynchronize(s));
+            } catch (...) {
+                cudaStreamSynchronize(s2);
+                for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+                cudaStreamDestroy(s2);
+                throw;
+            }
+            for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+            cudaStreamDestroy(s2);
+            return;
+        }
         run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
                     dmask.dev, 0, fm_dev, nullptr, status, nullptr, stats, s);
         Out<double> dftle(ftle_out, (size_t)rows_out * ny, s);

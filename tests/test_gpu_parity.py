@@ -513,3 +513,31 @@ def test_large_grid_properties(nb):
     # mean accepted / rejected steps as the survey measured for C1 (13.0 / 3.4)
     acc, rej = info["stats"][1] / (nx * ny), info["stats"][2] / (nx * ny)
     assert 12.0 < acc < 14.5 and 2.5 < rej < 4.5
+
+
+def test_pipelined_host_path_equals_device_path(nb):
+    """Large grid with host outputs: b200cs_flowmap_ftle_grid_2d integrates in row chunks and
+    streams finished rows out; the result must be bit-identical to the one-shot device path."""
+    torch = pytest.importorskip("torch")
+    nx, ny = 2600, 1700
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    mask = np.zeros((nx, ny), bool)
+    mask[100:140, 200:260] = True
+    info = {}
+    fm_h, ft_h = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -4.0, x, y, p, dx, dy, mask=mask, info=info)
+    xd, yd = torch.tensor(x, device="cuda"), torch.tensor(y, device="cuda")
+    fm_d = nb.integration.flowmap_grid_2D(f, 0.0, -4.0, xd, yd, p, mask=torch.tensor(mask, device="cuda"))
+    ft_d = nb.diagnostics.ftle_grid_2D(fm_d, -4.0, dx, dy, mask=torch.tensor(mask, device="cuda"))
+    assert np.array_equal(fm_h, fm_d.cpu().numpy())
+    assert np.array_equal(ft_h, ft_d.cpu().numpy())
+    assert (info["status"][~mask] == 1).all() and (info["status"][mask] == 0).all()
+    assert info["stats"][1] > 0
+    # FTLE only (no flow-map download) and halo rows
+    _, ft_only = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -4.0, x, y, p, dx, dy, mask=mask, return_flowmap=False)
+    assert np.array_equal(ft_only, ft_h)
+    _, ft_halo = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -4.0, x[300:2500], y, p, dx, dy, return_flowmap=False,
+                                                     halo=(1, 1))
+    _, ft_full = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -4.0, x, y, p, dx, dy, return_flowmap=False)
+    assert np.array_equal(ft_halo, ft_full[301:2499])
