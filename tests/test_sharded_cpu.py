@@ -87,3 +87,22 @@ def test_row_block_partition():
             assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
             sizes = [b - a for a, b in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_balanced_row_blocks():
+    from numbacs_b200.sharded import balanced_row_blocks
+    rng = np.random.default_rng(0)
+    for nx in (8, 100, 16384):
+        cost = 10 + 5 * np.sin(np.linspace(0, 6, nx)) + rng.random(nx)
+        for world in (1, 2, 3, 8):
+            blocks = balanced_row_blocks(cost, world)
+            assert len(blocks) == world and blocks[0][0] == 0 and blocks[-1][1] == nx
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            if nx >= 100:
+                sums = np.array([cost[a:b].sum() for a, b in blocks])
+                assert sums.max() / sums.mean() < 1.0 + 2.0 * cost.max() * world / cost.sum()
+    # uniform cost -> (almost) equal sizes; degenerate inputs stay valid
+    sizes = [b - a for a, b in balanced_row_blocks(np.ones(1000), 8)]
+    assert max(sizes) - min(sizes) <= 1
+    assert balanced_row_blocks(np.ones(2), 4)[-1][1] == 2
+    assert balanced_row_blocks(np.zeros(0), 3) == [(0, 0)] * 3
