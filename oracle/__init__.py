@@ -11,6 +11,9 @@ reference's Python call signatures so that parity tests read like the reference'
     get_flow_2D           flows.py:121    get_callable_scalar(_linear)  flows.py:387, 601
     flowmap / flowmap_n / flowmap_grid_2D / flowmap_n_grid_2D   integration.py:7, 64, 123, 467
     ftle_grid_2D / lavd_grid_2D           diagnostics.py:21, 272
+    flowmap_aux_grid_2D                   integration.py:249
+    C_tensor_2D / C_eig_aux_2D / C_eig_2D / ftle_from_eig   diagnostics.py:68, 115, 200, 247
+    ftle_ridge_pts / _ftle_ridge_pts_connect                extraction/ridges.py:9, 232
     composite_simpsons                    utils.py:611
 """
 import ctypes as C
@@ -75,6 +78,24 @@ def lib():
         L.oracle_lavd_grid_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
                                           C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double,
                                           C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_flowmap_aux_grid_2d.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                                 C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                                 C.c_double, C.c_int, C.c_int, C.c_double,
+                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p]
+        L.oracle_c_tensor_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                         C.c_void_p, C.c_void_p]
+        L.oracle_eigh2.argtypes = [C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+        L.oracle_c_eig_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_double,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oracle_c_eig_aux_2d.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double,
+                                          C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                          C.c_void_p]
+        L.oracle_ftle_from_eig.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
+        L.oracle_ftle_ridge_pts.restype = C.c_int64
+        L.oracle_ftle_ridge_pts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
+                                            C.c_void_p, C.c_double, C.c_double, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -304,3 +325,76 @@ def lavd_grid_2D(flowmap_n, tspan, T, vort_interp, xrav, yrav, period_x=0.0, per
                               int(vort_interp.linear), _ptr(xrav), _ptr(yrav), float(period_x),
                               float(period_y), _ptr(m), _ptr(out))
     return out
+
+
+def flowmap_aux_grid_2D(flow, t0, T, x, y, params, h=1e-5, eig_main=True, compute_edge=True,
+                        method="dop853", rtol=1e-6, atol=1e-8, mask=None, full=False):
+    x, y, params = _f64(x), _f64(y), _f64(params)
+    nx, ny = len(x), len(y)
+    n_aux = 5 if eig_main else 4
+    out = np.zeros((nx, ny, n_aux, 2))
+    status = np.zeros((nx, ny, n_aux), np.int32)
+    steps = np.zeros((nx, ny, n_aux, 2), np.int32)
+    stats = np.zeros(3, np.int64)
+    m = _mask(mask)
+    lib().oracle_flowmap_aux_grid_2d(flow.handle, float(t0), float(T), _ptr(x), nx, _ptr(y), ny,
+                                     _ptr(params), float(h), int(eig_main), int(compute_edge),
+                                     float(rtol), float(atol), _ptr(m), _ptr(out), _ptr(status),
+                                     _ptr(steps), _ptr(stats))
+    return (out, status, steps, stats) if full else out
+
+
+def C_tensor_2D(flowmap_aux, dx, dy, h=1e-5, mask=None):
+    fa = _f64(flowmap_aux)
+    nx, ny, n_aux = fa.shape[:3]
+    out = np.zeros((nx, ny, 3))
+    m = _mask(mask)
+    lib().oracle_c_tensor_2d(_ptr(fa), nx, ny, n_aux, float(h), _ptr(m), _ptr(out))
+    return out
+
+
+def eigh2(a, b, c):
+    w, v = np.zeros(2), np.zeros((2, 2))
+    lib().oracle_eigh2(float(a), float(b), float(c), _ptr(w), _ptr(v))
+    return w, v
+
+
+def C_eig_2D(flowmap, dx, dy, mask=None):
+    fm = _f64(flowmap)
+    nx, ny = fm.shape[:2]
+    vals, vecs = np.zeros((nx, ny, 2)), np.zeros((nx, ny, 2, 2))
+    m = _mask(mask)
+    lib().oracle_c_eig_2d(_ptr(fm), nx, ny, float(dx), float(dy), _ptr(m), _ptr(vals), _ptr(vecs))
+    return vals, vecs
+
+
+def C_eig_aux_2D(flowmap_aux, dx, dy, h=1e-5, eig_main=True, mask=None):
+    fa = _f64(flowmap_aux)
+    nx, ny, n_aux = fa.shape[:3]
+    vals, vecs = np.zeros((nx, ny, 2)), np.zeros((nx, ny, 2, 2))
+    m = _mask(mask)
+    lib().oracle_c_eig_aux_2d(_ptr(fa), nx, ny, n_aux, float(dx), float(dy), float(h),
+                              int(eig_main), _ptr(m), _ptr(vals), _ptr(vecs))
+    return vals, vecs
+
+
+def ftle_from_eig(eigval_max, T):
+    e = _f64(eigval_max)
+    out = np.zeros(e.shape)
+    lib().oracle_ftle_from_eig(_ptr(e), e.size, float(T), _ptr(out))
+    return out
+
+
+def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
+    f, ev, x, y = _f64(f), _f64(eigvec_max), _f64(x), _f64(y)
+    nx, ny = f.shape
+    f_min = 0.0 if percentile == 0 else float(np.percentile(f, percentile))
+    r_pts, r_vec, sdd = np.zeros((nx * ny, 3)), np.zeros((nx * ny, 2)), np.zeros(nx * ny)
+    lib().oracle_ftle_ridge_pts(_ptr(f), _ptr(ev), nx, ny, _ptr(x), _ptr(y), float(sdd_thresh),
+                                f_min, _ptr(r_pts), _ptr(r_vec), _ptr(sdd))
+    return r_pts, r_vec, sdd, min(x[1] - x[0], y[1] - y[0])
+
+
+def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
+    r_pts, _, sdd, _ = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)
+    return r_pts[sdd < -sdd_thresh][:, :2]  # sdd is c2 (< -sdd_thresh <= 0) at ridge points, else 0

@@ -12,6 +12,11 @@
  *   - particle loops                         src/numbacs/integration.py:7-61, 64-120, 123-182, 467-533
  *   - FTLE                                   src/numbacs/diagnostics.py:21-65, utils.py:9-46, 168-189
  *   - LAVD + composite Simpson               src/numbacs/diagnostics.py:272-379, utils.py:611-655
+ *   - aux-grid flow map                      src/numbacs/integration.py:249-464
+ *   - Cauchy-Green tensor / eigen-pairs      src/numbacs/diagnostics.py:68-269, utils.py:49-124
+ *     (np.linalg.eigh on 2x2 = LAPACK dlaev2, restated; pinned by Cevals/Cevecs*.npy and by the
+ *     live numbacs.diagnostics.C_eig_2D, which imports here)
+ *   - FTLE ridge points                      src/numbacs/extraction/ridges.py:9-76, 232-318
  *
  * The arithmetic of the ODE solver and of the spline is NOT in the reference tree: it lives in
  * the third-party packages `numbalsoda` (unpinned, pyproject.toml:32) and `interpolation>=2.2.6`
@@ -665,6 +670,218 @@ void oracle_lavd_grid_2d(const double *fm_n, int64_t nx, int64_t ny, int64_t n, 
         free(integrand);
     }
     free(vavg);
+}
+
+/* ------------------------------------------------------------------ aux grid, Cauchy-Green tensor, ridges */
+
+/* flowmap_aux_grid_2D (integration.py:249-464): final positions over the auxiliary stencil
+ * (x_i +- h, y_j), (x_i, y_j +- h) [, (x_i, y_j) when eig_main], out[nx, ny, n_aux, 2].
+ * Which entries are integrated (everything else stays 0):
+ *   eig_main, compute_edge : edge cells (i or j on the border) only the centre point k = 4
+ *                            (integration.py:320-343), interior cells all five (345-355)
+ *   eig_main, !compute_edge: interior cells only, all five (356-369)
+ *   !eig_main              : all four points on [0, nx) x [0, ny) or the interior (425-446) */
+int oracle_flowmap_aux_grid_2d(const flow_t *f, double t0, double T, const double *x, int64_t nx,
+                               const double *y, int64_t ny, const double *params, double h,
+                               int eig_main, int compute_edge, double rtol, double atol,
+                               const uint8_t *mask, double *out, int32_t *status, int32_t *steps,
+                               int64_t *stats)
+{
+    const int n_aux = eig_main ? 5 : 4;
+    const double aux[5][2] = {{h, 0.0}, {-h, 0.0}, {0.0, h}, {0.0, -h}, {0.0, 0.0}};
+    int64_t npts = nx * ny * n_aux;
+    double *pts = (double *)malloc(sizeof(double) * 2 * npts);
+    uint8_t *m = (uint8_t *)malloc(npts);
+    for (int64_t i = 0; i < nx; ++i)
+        for (int64_t j = 0; j < ny; ++j) {
+            int edge = (i == 0 || i == nx - 1 || j == 0 || j == ny - 1);
+            for (int k = 0; k < n_aux; ++k) {
+                int64_t q = (i * ny + j) * n_aux + k;
+                pts[2 * q] = x[i] + aux[k][0];
+                pts[2 * q + 1] = y[j] + aux[k][1];
+                int on = !(mask && mask[i * ny + j]);
+                if (edge) on = on && compute_edge && (!eig_main || k == 4);
+                m[q] = (uint8_t)!on;
+            }
+        }
+    int rc = oracle_flowmap_pts(f, t0, T, pts, npts, params, rtol, atol, m, 2, 1, out, NULL, status,
+                                steps, stats);
+    free(pts);
+    free(m);
+    return rc;
+}
+
+/* gradF_aux_stencil_2D (utils.py:49-84) */
+static inline void grad_aux(const double *fa, int64_t ny, int n_aux, int64_t i, int64_t j, double h,
+                            double *g)
+{
+    const double *c = fa + ((i * ny + j) * n_aux) * 2;
+    g[0] = (c[0] - c[2]) / (2 * h);  /* dFxdx */
+    g[1] = (c[4] - c[6]) / (2 * h);  /* dFxdy */
+    g[2] = (c[1] - c[3]) / (2 * h);  /* dFydx */
+    g[3] = (c[5] - c[7]) / (2 * h);  /* dFydy */
+}
+
+/* C_tensor_2D (diagnostics.py:68-112): C11, C12, C22 on [2, nx-2) x [2, ny-2) */
+void oracle_c_tensor_2d(const double *fm_aux, int64_t nx, int64_t ny, int n_aux, double h,
+                        const uint8_t *mask, double *C)
+{
+    memset(C, 0, sizeof(double) * nx * ny * 3);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 2; i < nx - 2; ++i)
+        for (int64_t j = 2; j < ny - 2; ++j) {
+            if (mask && mask[i * ny + j]) continue;
+            double g[4];
+            grad_aux(fm_aux, ny, n_aux, i, j, h, g);
+            double *c = C + (i * ny + j) * 3;
+            c[0] = g[0] * g[0] + g[2] * g[2];
+            c[1] = g[0] * g[1] + g[2] * g[3];
+            c[2] = g[1] * g[1] + g[3] * g[3];
+        }
+}
+
+/* np.linalg.eigh / eigvalsh of the symmetric 2x2 matrix [[a, b], [b, c]] as LAPACK computes it
+ * (numba and numpy both call ?syevd, uplo 'L'; for n = 2 the tridiagonal reduction is the
+ * identity and dsteqr / dsterf either split the matrix when |b| <= sqrt|a| sqrt|c| eps or call
+ * dlaev2 / dlae2 once).  dlaev2 is restated from the LAPACK reference documentation; the
+ * column / sign conventions were checked against numpy on 20000 random matrices (bit-exact,
+ * same signs).  w ascending, v[r][col]: column `col` is the eigenvector of w[col]. */
+void oracle_eigh2(double a, double b, double c, double *w, double *v)
+{
+    const double eps = 1.1102230246251565e-16; /* dlamch('E') */
+    if (b == 0.0 || fabs(b) <= (sqrt(fabs(a)) * sqrt(fabs(c))) * eps) {
+        if (a <= c) { w[0] = a; w[1] = c; v[0] = 1; v[1] = 0; v[2] = 0; v[3] = 1; }
+        else        { w[0] = c; w[1] = a; v[0] = 0; v[1] = 1; v[2] = 1; v[3] = 0; }
+        return;
+    }
+    double sm = a + c, df = a - c, adf = fabs(df), tb = b + b, ab = fabs(tb);
+    double acmx, acmn, rt, rt1, rt2, cs1, sn1;
+    int sgn1, sgn2;
+    if (fabs(a) > fabs(c)) { acmx = a; acmn = c; } else { acmx = c; acmn = a; }
+    if (adf > ab) { double q = ab / adf; rt = adf * sqrt(1.0 + q * q); }
+    else if (adf < ab) { double q = adf / ab; rt = ab * sqrt(1.0 + q * q); }
+    else rt = ab * sqrt(2.0);
+    if (sm < 0.0) { rt1 = 0.5 * (sm - rt); sgn1 = -1; rt2 = (acmx / rt1) * acmn - (b / rt1) * b; }
+    else if (sm > 0.0) { rt1 = 0.5 * (sm + rt); sgn1 = 1; rt2 = (acmx / rt1) * acmn - (b / rt1) * b; }
+    else { rt1 = 0.5 * rt; rt2 = -0.5 * rt; sgn1 = 1; }
+    double cs;
+    if (df >= 0.0) { cs = df + rt; sgn2 = 1; } else { cs = df - rt; sgn2 = -1; }
+    if (fabs(cs) > ab) { double ct = -tb / cs; sn1 = 1.0 / sqrt(1.0 + ct * ct); cs1 = ct * sn1; }
+    else if (ab == 0.0) { cs1 = 1.0; sn1 = 0.0; }
+    else { double tn = -cs / tb; cs1 = 1.0 / sqrt(1.0 + tn * tn); sn1 = tn * cs1; }
+    if (sgn1 == sgn2) { double tn = cs1; cs1 = -sn1; sn1 = tn; }
+    /* (cs1, sn1) is the unit eigenvector of rt1, the eigenvalue of larger absolute value */
+    if (rt1 >= rt2) { w[0] = rt2; w[1] = rt1; v[0] = -sn1; v[1] = cs1; v[2] = cs1; v[3] = sn1; }
+    else            { w[0] = rt1; w[1] = rt2; v[0] = cs1; v[1] = -sn1; v[2] = sn1; v[3] = cs1; }
+}
+
+/* C_eig_2D (diagnostics.py:200-244): eigvals[nx,ny,2] ascending, eigvecs[nx,ny,2,2] */
+void oracle_c_eig_2d(const double *fm, int64_t nx, int64_t ny, double dx, double dy,
+                     const uint8_t *mask, double *eigvals, double *eigvecs)
+{
+    memset(eigvals, 0, sizeof(double) * nx * ny * 2);
+    memset(eigvecs, 0, sizeof(double) * nx * ny * 4);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 1; i < nx - 1; ++i)
+        for (int64_t j = 1; j < ny - 1; ++j) {
+            if (mask && mask[i * ny + j]) continue;
+#define F(I, J, C) fm[(((I)*ny) + (J)) * 2 + (C)]
+            double dxdx = (F(i + 1, j, 0) - F(i - 1, j, 0)) / (2 * dx);
+            double dxdy = (F(i, j + 1, 0) - F(i, j - 1, 0)) / (2 * dy);
+            double dydx = (F(i + 1, j, 1) - F(i - 1, j, 1)) / (2 * dx);
+            double dydy = (F(i, j + 1, 1) - F(i, j - 1, 1)) / (2 * dy);
+#undef F
+            double off = dxdx * dxdy + dydx * dydy;
+            oracle_eigh2(dxdx * dxdx + dydx * dydx, off, dxdy * dxdy + dydy * dydy,
+                         eigvals + (i * ny + j) * 2, eigvecs + (i * ny + j) * 4);
+        }
+}
+
+/* C_eig_aux_2D (diagnostics.py:115-197): eig_main -> eigenvalues of the main-grid tensor
+ * (gradF_main_stencil_2D on the centre points, utils.py:87-124), eigenvectors of the aux-grid
+ * tensor, on [2, nx-2) x [2, ny-2); otherwise both from the aux grid on [1, nx-1) x [1, ny-1) */
+void oracle_c_eig_aux_2d(const double *fm_aux, int64_t nx, int64_t ny, int n_aux, double dx,
+                         double dy, double h, int eig_main, const uint8_t *mask, double *eigvals,
+                         double *eigvecs)
+{
+    memset(eigvals, 0, sizeof(double) * nx * ny * 2);
+    memset(eigvecs, 0, sizeof(double) * nx * ny * 4);
+    int64_t lo = eig_main ? 2 : 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = lo; i < nx - lo; ++i)
+        for (int64_t j = lo; j < ny - lo; ++j) {
+            if (mask && mask[i * ny + j]) continue;
+            double g[4], w[2], v[4];
+            grad_aux(fm_aux, ny, n_aux, i, j, h, g);
+            oracle_eigh2(g[0] * g[0] + g[2] * g[2], g[0] * g[1] + g[2] * g[3],
+                         g[1] * g[1] + g[3] * g[3], w, v);
+            if (eig_main) {
+#define FA(I, J, C) fm_aux[((((I)*ny) + (J)) * n_aux + (n_aux - 1)) * 2 + (C)]
+                double dxdx = (FA(i + 1, j, 0) - FA(i - 1, j, 0)) / (2 * dx);
+                double dxdy = (FA(i, j + 1, 0) - FA(i, j - 1, 0)) / (2 * dy);
+                double dydx = (FA(i + 1, j, 1) - FA(i - 1, j, 1)) / (2 * dx);
+                double dydy = (FA(i, j + 1, 1) - FA(i, j - 1, 1)) / (2 * dy);
+#undef FA
+                double vm[4];
+                oracle_eigh2(dxdx * dxdx + dydx * dydx, dxdx * dxdy + dydx * dydy,
+                             dxdy * dxdy + dydy * dydy, w, vm);
+            }
+            for (int k = 0; k < 2; ++k) eigvals[(i * ny + j) * 2 + k] = w[k];
+            for (int k = 0; k < 4; ++k) eigvecs[(i * ny + j) * 4 + k] = v[k];
+        }
+}
+
+/* ftle_from_eig (diagnostics.py:247-269) */
+void oracle_ftle_from_eig(const double *eigval_max, int64_t n, double T, double *ftle)
+{
+    for (int64_t q = 0; q < n; ++q)
+        ftle[q] = (eigval_max[q] > 1) ? log(eigval_max[q]) / (2 * fabs(T)) : 0.0;
+}
+
+/* _ftle_ridge_pts_connect (extraction/ridges.py:232-318), which is ftle_ridge_pts (9-76) plus the
+ * per-pixel eigenvector and second directional derivative: r_pts[nx*ny, 3] (-1 where no ridge
+ * point), r_vec[nx*ny, 2], sdd[nx*ny].  f_min is 0 or np.percentile(f, percentile), computed by
+ * the caller.  Returns the number of ridge points. */
+int64_t oracle_ftle_ridge_pts(const double *f, const double *evec, int64_t nx, int64_t ny,
+                              const double *x, const double *y, double sdd_thresh, double f_min,
+                              double *r_pts, double *r_vec, double *sdd)
+{
+    double dx = x[1] - x[0], dy = y[1] - y[0];
+    for (int64_t q = 0; q < nx * ny; ++q) {
+        r_pts[3 * q] = r_pts[3 * q + 1] = r_pts[3 * q + 2] = -1.0;
+        r_vec[2 * q] = r_vec[2 * q + 1] = 0.0;
+        sdd[q] = 0.0;
+    }
+    int64_t count = 0;
+#pragma omp parallel for schedule(static) reduction(+ : count)
+    for (int64_t i = 2; i < nx - 2; ++i)
+        for (int64_t j = 2; j < ny - 2; ++j) {
+#define F(I, J) f[(I)*ny + (J)]
+            double f0 = F(i, j);
+            if (!(f0 > f_min)) continue;
+            double fx = (F(i + 1, j) - F(i - 1, j)) / (2 * dx);
+            double fy = (F(i, j + 1) - F(i, j - 1)) / (2 * dy);
+            double fxx = (F(i + 1, j) - 2 * F(i, j) + F(i - 1, j)) / (dx * dx);
+            double fyy = (F(i, j + 1) - 2 * F(i, j) + F(i, j - 1)) / (dy * dy);
+            double fxy = (F(i + 1, j + 1) - F(i + 1, j - 1) - F(i - 1, j + 1) + F(i - 1, j - 1)) /
+                         (4 * dx * dy);
+#undef F
+            double ex = evec[(i * ny + j) * 2], ey = evec[(i * ny + j) * 2 + 1];
+            double c2 = ex * (fxx * ex + fxy * ey) + ey * (fxy * ex + fyy * ey);
+            if (c2 < -sdd_thresh) {
+                double t = -(fx * ex + fy * ey) / c2;
+                if (fabs(t * ex) <= dx / 2 && fabs(t * ey) <= dy / 2) {
+                    int64_t k = i * ny + j;
+                    r_pts[3 * k] = x[i] + t * ex;
+                    r_pts[3 * k + 1] = y[j] + t * ey;
+                    r_vec[2 * k] = ex;
+                    r_vec[2 * k + 1] = ey;
+                    sdd[k] = c2;
+                    ++count;
+                }
+            }
+        }
+    return count;
 }
 
 /* ------------------------------------------------------------------ helpers ------------ */

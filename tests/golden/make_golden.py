@@ -13,7 +13,9 @@ frozen here as small arrays:
      the scalar KATs in tests/test_utils.py -- pulled out with `ast`, never retyped;
  (3) outputs of the REAL reference code that imports here (numbacs.diagnostics.ftle_grid_2D,
      numbacs.utils.composite_simpsons / eigvalsh_max_2D run from /root/reference/src) on seeded
-     float64 inputs, so FTLE parity is checked beyond float32 resolution.
+     float64 inputs, so FTLE parity is checked beyond float32 resolution;
+ (4) likewise numbacs.diagnostics.{C_eig_2D, C_tensor_2D, C_eig_aux_2D, ftle_from_eig} and the
+     ridge-point stencil of numbacs/extraction/ridges.py.
 
 Nothing in this script is used at test time; only the .npz is.
 """
@@ -46,7 +48,8 @@ def literal_arrays(path, func_name, var_names):
 def main():
     G = {}
     td = os.path.join(REF, "tests", "testing_data")
-    for name in ("fm", "fm_n", "ftle", "lavd", "vort"):
+    for name in ("fm", "fm_n", "ftle", "lavd", "vort", "fm_aux", "C", "Cevals", "Cevecs",
+                 "Cevals_aux", "Cevecs_aux", "ridge_pts"):
         G["ref_" + name] = np.load(os.path.join(td, name + ".npy"))
 
     tf = os.path.join(REF, "tests", "test_flows.py")
@@ -89,6 +92,45 @@ def main():
     A = np.array([[2.5, -1.25], [-1.25, 0.75]])
     G["eig_in"] = A
     G["eig_out"] = np.array([eigvalsh_max_2D(A)])
+
+    # (4) the Cauchy-Green tensor / eigen-pair functions (real numbacs.diagnostics code) and the
+    # ridge-point stencil (real numbacs/extraction/ridges.py, loaded without the package
+    # __init__, which needs the missing `interpolation` package) on seeded float64 inputs
+    import importlib.util
+    import types
+    from numbacs.diagnostics import C_eig_2D, C_eig_aux_2D, C_tensor_2D, ftle_from_eig
+
+    fm3 = rng.normal(size=(23, 19, 2)) * 3.0
+    fa3 = rng.normal(size=(23, 19, 5, 2)) * 1e-4
+    mask3 = rng.random((23, 19)) < 0.2
+    G["ceig_in"], G["caux_in"], G["ceig_mask"] = fm3, fa3, mask3
+    G["ceig_args"] = np.array([0.1, 0.07, 1e-5])  # dx, dy, h
+    for tag, m in (("", None), ("_masked", mask3)):
+        G["ceig_vals" + tag], G["ceig_vecs" + tag] = C_eig_2D(fm3, 0.1, 0.07, m)
+        G["ctensor" + tag] = C_tensor_2D(fa3, 0.1, 0.07, 1e-5, m)
+        G["caux_vals_main" + tag], G["caux_vecs_main" + tag] = C_eig_aux_2D(fa3, 0.1, 0.07, 1e-5, True, m)
+        G["caux_vals" + tag], G["caux_vecs" + tag] = C_eig_aux_2D(fa3[:, :, :4], 0.1, 0.07, 1e-5, False, m)
+    G["ftle_from_eig_out"] = ftle_from_eig(G["ceig_vals"][:, :, 1], -3.0)
+
+    pkg = types.ModuleType("numbacs.extraction")
+    pkg.__path__ = [os.path.join(REF, "src", "numbacs", "extraction")]
+    sys.modules["numbacs.extraction"] = pkg
+    spec = importlib.util.spec_from_file_location(
+        "numbacs.extraction.ridges", os.path.join(pkg.__path__[0], "ridges.py"))
+    ridges = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = ridges
+    spec.loader.exec_module(ridges)
+    xr, yr = np.linspace(0, 2, 60), np.linspace(0, 1, 45)
+    X, Y = np.meshgrid(xr, yr, indexing="ij")
+    f = np.sin(3 * X + Y * Y) * np.cos(2 * Y) + 0.03 * rng.normal(size=X.shape) + 0.5
+    th = rng.uniform(0, 2 * np.pi, size=X.shape)
+    ev = np.stack([np.cos(th), np.sin(th)], -1)
+    G["ridge_f"], G["ridge_ev"], G["ridge_x"], G["ridge_y"] = f, ev, xr, yr
+    for tag, (thr, pct) in (("a", (0.0, 0)), ("b", (10.0, 0)), ("c", (0.0, 60))):
+        G["ridge_pts_" + tag] = ridges.ftle_ridge_pts(f, ev, xr, yr, thr, pct)
+        rp, rv, sdd, hmin = ridges._ftle_ridge_pts_connect(f, ev, xr, yr, thr, pct)
+        G["ridge_conn_pts_" + tag], G["ridge_conn_vec_" + tag], G["ridge_conn_sdd_" + tag] = rp, rv, sdd
+    G["ridge_args"] = np.array([[0.0, 0], [10.0, 0], [0.0, 60]])
 
     out = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(out, **G)
