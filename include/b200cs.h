@@ -193,6 +193,68 @@ B200CS_API int b200cs_lavd_flowmap_grid_2d(int flow, double t0, double T, const 
 B200CS_API int b200cs_lavd_vort_sums(int vort, const double *tspan, int64_t n, const double *xrav,
                           const double *yrav, int64_t nrav, double *sums /*[n]*/, void *stream);
 
+/* ---- aux grid, Cauchy-Green tensor, eigen-pairs, ridge points ------------------------------- */
+
+/* flowmap_aux_grid_2D(funcptr, t0, T, x, y, params, h, eig_main, compute_edge, method, rtol, atol,
+ *                     mask)                                   (integration.py:249-464)
+ * Final positions over the auxiliary stencil (x_i +- h, y_j), (x_i, y_j +- h) and, with eig_main,
+ * the grid point itself: out is [nx, ny, n_aux, 2] with n_aux = eig_main ? 5 : 4.  Entries the
+ * reference does not integrate stay 0: masked cells; with eig_main the four stencil points of
+ * edge cells (only their centre point is integrated, and only if compute_edge); without
+ * compute_edge every edge cell.  status is [nx, ny, n_aux], steps [nx, ny, n_aux, 2]. */
+B200CS_API int b200cs_flowmap_aux_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
+                               const double *y, int64_t ny, const double *params, int nparams,
+                               double h, int eig_main, int compute_edge, int method, double rtol,
+                               double atol, const uint8_t *mask, double *out, int32_t *status,
+                               int32_t *steps, int64_t *stats, void *stream);
+
+/* C_tensor_2D(flowmap_aux, dx, dy, h, mask)    (diagnostics.py:68-112; utils.py:49-84)
+ * C[nx, ny, 3] = (C11, C12, C22) on [2, nx-2) x [2, ny-2), 0 elsewhere; dx, dy unused as in the
+ * reference. */
+B200CS_API int b200cs_c_tensor_2d(const double *flowmap_aux /*[nx,ny,n_aux,2]*/, int64_t nx, int64_t ny,
+                       int n_aux, double dx, double dy, double h, const uint8_t *mask,
+                       double *C /*[nx,ny,3]*/, void *stream);
+
+/* C_eig_2D(flowmap, dx, dy, mask)              (diagnostics.py:200-244)
+ * eigvals[nx, ny, 2] ascending, eigvecs[nx, ny, 2, 2] (column c belongs to eigvals[..., c]) as
+ * np.linalg.eigh returns them (LAPACK dlaev2 conventions, signs included); interior pixels only. */
+B200CS_API int b200cs_c_eig_2d(const double *flowmap /*[nx,ny,2]*/, int64_t nx, int64_t ny, double dx,
+                    double dy, const uint8_t *mask, double *eigvals, double *eigvecs, void *stream);
+
+/* C_eig_aux_2D(flowmap_aux, dx, dy, h, eig_main, mask)   (diagnostics.py:115-197; utils.py:49-124)
+ * eig_main: eigenvalues from the main-grid tensor (centre points), eigenvectors from the aux-grid
+ * tensor, on [2, nx-2) x [2, ny-2); otherwise both from the aux grid on [1, nx-1) x [1, ny-1). */
+B200CS_API int b200cs_c_eig_aux_2d(const double *flowmap_aux, int64_t nx, int64_t ny, int n_aux, double dx,
+                        double dy, double h, int eig_main, const uint8_t *mask, double *eigvals,
+                        double *eigvecs, void *stream);
+
+/* ftle_from_eig(eigval_max, T)                 (diagnostics.py:247-269)
+ * eigval_max is read with a stride (in doubles) so that eigvals[:, :, 1] can be passed in place:
+ * ftle[q] = log(eigval_max[q*stride]) / (2|T|) where > 1, else 0. */
+B200CS_API int b200cs_ftle_from_eig(const double *eigval_max, int64_t n, int64_t stride, double T,
+                         double *ftle /*[n]*/, void *stream);
+
+/* ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh, percentile)          (extraction/ridges.py:9-76)
+ * _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)  (ridges.py:232-318)
+ * eigvec_max[i, j, c] is read at eigvec_max[(i*ny + j)*ev_pixel_stride + c*ev_comp_stride] so that
+ * eigvecs[:, :, :, 1] (strides 4, 2) can be passed in place.  f_min = 0 or np.percentile(f, p)
+ * (from b200cs_order_stats).  All outputs are nullable:
+ *   r_pts [nx*ny, 3], r_vec [nx*ny, 2], sdd [nx*ny]  per-pixel arrays of the _connect form
+ *       (r_pts rows are -1 where there is no ridge point, the third column is the reference's
+ *        ridge-number placeholder -1)
+ *   pts_compact [capacity, 2] + count: the ridge points in raveled-pixel order
+ *       (r_pts[ridge_bool, :]); *count receives the total number found even when it exceeds
+ *       capacity (call with pts_compact = NULL first to size the buffer). */
+B200CS_API int b200cs_ftle_ridge_pts(const double *ftle /*[nx,ny]*/, const double *eigvec_max,
+                          int64_t ev_pixel_stride, int64_t ev_comp_stride, int64_t nx, int64_t ny,
+                          const double *x, const double *y, double sdd_thresh, double f_min,
+                          double *r_pts, double *r_vec, double *sdd, double *pts_compact,
+                          int64_t capacity, int64_t *count, void *stream);
+
+/* out2 = { sorted(data)[k], sorted(data)[min(k+1, n-1)] } by radix select (no sort, data is not
+ * modified): the two order statistics np.percentile interpolates between (ridges.py:45, 279). */
+B200CS_API int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream);
+
 /* ---- measurement helper -------------------------------------------------------------------- */
 
 /* register-resident DFMA chains on every SM for `iters` iterations; returns achieved FP64

@@ -18,7 +18,8 @@ OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libb200cs.so")
 
 SOURCES = ["capi.cu", "flowmap_dispatch.cu", "flowmap_dg.cu", "flowmap_bickley.cu",
-           "flowmap_abc.cu", "flowmap_spline.cu", "ftle_kernels.cu", "diag_kernels.cu"]
+           "flowmap_abc.cu", "flowmap_spline.cu", "ftle_kernels.cu", "diag_kernels.cu",
+           "tensor_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 
@@ -39,19 +40,20 @@ def _deps_mtime():
     return m
 
 
-def build(force=False, verbose=False):
-    """Compile (if stale) and return the path of libb200cs.so."""
+def build(force=False, verbose=False, extra_flags=(), lib=LIB, objdir=OBJ):
+    """Compile (if stale) and return the path of libb200cs.so.  `extra_flags` / `lib` / `objdir`
+    build an experimental variant next to the product library (tools/build_variant.py)."""
     newest = _deps_mtime()
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
-        return LIB
-    os.makedirs(OBJ, exist_ok=True)
+    if not force and os.path.exists(lib) and os.path.getmtime(lib) >= newest:
+        return lib
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ, src[:-3] + ".o")
+        obj = os.path.join(objdir, src[:-3] + ".o")
         if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
             return obj
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + \
               ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
@@ -62,12 +64,12 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nvcc, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":

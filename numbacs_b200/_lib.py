@@ -10,7 +10,9 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200cs.so")
+# B200CS_LIB selects an experimental build of the same library (tools/build_variant.py, A/B kernel
+# measurements); the product path is the in-tree libb200cs.so
+LIB_PATH = os.environ.get("B200CS_LIB") or os.path.join(_HERE, "libb200cs.so")
 
 E_INVALID, E_CUDA, E_HANDLE, E_UNSUPPORTED = -1, -2, -3, -4
 FLOW_KINDS = {"double_gyre": 0, "bickley_jet": 1, "abc": 2}
@@ -45,6 +47,15 @@ PROTOTYPES = {
     "b200cs_lavd_flowmap_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp, _i, _i, _d, _d,
                                     _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "b200cs_lavd_vort_sums": [_i, _vp, _i64, _vp, _vp, _i64, _vp, _vp],
+    "b200cs_flowmap_aux_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _d, _i, _i, _i, _d, _d,
+                                   _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200cs_c_tensor_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
+    "b200cs_c_eig_2d": [_vp, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp],
+    "b200cs_c_eig_aux_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp],
+    "b200cs_ftle_from_eig": [_vp, _i64, _i64, _d, _vp, _vp],
+    "b200cs_ftle_ridge_pts": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp,
+                              _i64, _vp, _vp],
+    "b200cs_order_stats": [_vp, _i64, _i64, _vp, _vp],
     "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
 }
 
@@ -115,6 +126,30 @@ def arg_in(a, dtype=np.float64):
         return Arg(t, C.c_void_p(t.data_ptr()), t.is_cuda)
     arr = np.ascontiguousarray(a, dtype=dtype)
     return Arg(arr, C.c_void_p(arr.ctypes.data), False)
+
+
+def _elem_strides(a):
+    """Strides in elements for numpy arrays and torch tensors alike."""
+    if _is_torch(a):
+        return tuple(int(v) for v in a.stride())
+    return tuple(int(v) // a.itemsize for v in a.strides)
+
+
+def strided_in(a):
+    """An array whose elements lie at a constant element stride in memory (a contiguous array, or
+    a last-axis slice like eigvals[:, :, 1] of a contiguous one) -> (Arg, stride); anything else
+    is copied to a contiguous buffer first."""
+    is_t = _is_torch(a)
+    if not is_t:
+        a = np.asarray(a)
+    ok = (a.dtype == np.float64) if not is_t else (str(a.dtype) == "torch.float64")
+    if ok and a.ndim >= 1 and all(int(v) > 0 for v in a.shape):
+        st, shape = _elem_strides(a), tuple(int(v) for v in a.shape)
+        s = st[-1]
+        if s >= 1 and all(st[d] == st[d + 1] * shape[d + 1] for d in range(a.ndim - 1)):
+            ptr = a.data_ptr() if is_t else a.ctypes.data
+            return Arg(a, C.c_void_p(ptr), bool(is_t and a.is_cuda)), s
+    return arg_in(a), 1
 
 
 def mask_in(mask):

@@ -125,11 +125,17 @@ static void check_device(const FlowSpec &f) {
 }
 
 // common body of flowmap_grid_2d / flowmap_pts
+struct AuxSpec {  // flowmap_aux_grid_2D only
+    int n_aux = 0;  // 0: not an aux-grid call
+    int edge = 0;
+    double h = 0.0;
+};
+
 static void run_flowmap(int flow, double t0, double T, bool grid_mode, const double *x, int64_t nx,
                         const double *y, int64_t ny, const double *pts, int64_t npts_in, int ndim,
                         const double *params, int nparams, int method, double rtol, double atol,
                         const uint8_t *mask, int n, double *out, double *tspan, int32_t *status,
-                        int32_t *steps, int64_t *stats, cudaStream_t s) {
+                        int32_t *steps, int64_t *stats, cudaStream_t s, AuxSpec aux = AuxSpec{}) {
     require_device();
     B2_REQUIRE(method == B200CS_METHOD_DOP853,
                "only method='dop853' is implemented on the GPU (got method id %d)", method);
@@ -138,7 +144,8 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     auto f = registry_get(flow);
     B2_REQUIRE(f->kind >= 0, "handle %d is a scalar field, not a flow", flow);
     check_device(*f);
-    const long long npts = grid_mode ? (long long)nx * ny : (long long)npts_in;
+    const long long ncell = grid_mode ? (long long)nx * ny : (long long)npts_in;
+    const long long npts = aux.n_aux ? ncell * aux.n_aux : ncell;
     B2_REQUIRE(npts >= 0, "negative particle count");
     if (grid_mode) B2_REQUIRE(f->ndim == 2, "grid entry points need a 2-D flow");
     else B2_REQUIRE(ndim == f->ndim, "pts has %d columns but the flow state is %d-D", ndim, f->ndim);
@@ -158,6 +165,9 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     A.nx = nx;
     A.ny = ny;
     A.npts = npts;
+    A.n_aux = aux.n_aux;
+    A.aux_edge = aux.edge;
+    A.aux_h = aux.h;
 
     if (tspan && n >= 2) {
         // returned times are params[0] * t_eval (integration.py:120, 533)
@@ -184,7 +194,7 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
         B2_REQUIRE(pts, "pts must not be null");
         dpts = In<double>(pts, (size_t)npts * nd, s);
     }
-    In<uint8_t> dmask(mask, npts, s);
+    In<uint8_t> dmask(mask, ncell, s);  // one byte per grid cell / point
     B2_REQUIRE(out, "out must not be null");
     Out<double> dout(out, (size_t)npts * row, s);
     Out<int32_t> dstatus(status, npts, s);
@@ -201,7 +211,7 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     A.steps = dsteps.dev;
     A.stats = reinterpret_cast<unsigned long long *>(dstats.dev);
 
-    launch_flowmap(*f, A, grid_mode, s);
+    launch_flowmap(*f, A, aux.n_aux ? 2 : (grid_mode ? 1 : 0), s);
 
     dout.download();
     dstatus.download();
@@ -671,6 +681,180 @@ int b200cs_lavd_flowmap_grid_2d(int flow, double t0, double T, const double *x, 
         dstats.download();
         if (dlavd.staged() || dfm.staged() || dstatus.staged() || dstats.staged())
             B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_flowmap_aux_grid_2d(int flow, double t0, double T, const double *x, int64_t nx, const double *y,
+                               int64_t ny, const double *params, int nparams, double h, int eig_main,
+                               int compute_edge, int method, double rtol, double atol,
+                               const uint8_t *mask, double *out, int32_t *status, int32_t *steps,
+                               int64_t *stats, void *stream) {
+    return guarded([&] {
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        AuxSpec aux;
+        aux.n_aux = eig_main ? 5 : 4;
+        aux.edge = compute_edge ? 1 : 0;
+        aux.h = h;
+        run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
+                    mask, 0, out, nullptr, status, steps, stats, static_cast<cudaStream_t>(stream), aux);
+    });
+}
+
+int b200cs_c_tensor_2d(const double *flowmap_aux, int64_t nx, int64_t ny, int n_aux, double dx, double dy,
+                       double h, const uint8_t *mask, double *C_out, void *stream) {
+    return guarded([&] {
+        require_device();
+        (void)dx;
+        (void)dy;  // unused by the reference too (diagnostics.py:68-112)
+        B2_REQUIRE(flowmap_aux && C_out, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE(n_aux == 4 || n_aux == 5, "n_aux must be 4 or 5 (got %d)", n_aux);
+        B2_REQUIRE(h != 0.0, "h must be non-zero");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfa(flowmap_aux, np * n_aux * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dout(C_out, np * 3, s);
+        launch_c_tensor(dfa.dev, nx, ny, n_aux, h, dmask.dev, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_c_eig_2d(const double *flowmap, int64_t nx, int64_t ny, double dx, double dy, const uint8_t *mask,
+                    double *eigvals, double *eigvecs, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmap && eigvals && eigvecs, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE(dx != 0.0 && dy != 0.0, "dx and dy must be non-zero");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmap, np * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dvals(eigvals, np * 2, s), dvecs(eigvecs, np * 4, s);
+        launch_c_eig(dfm.dev, nx, ny, 1, 0.0, dx, dy, /*aux_vecs=*/false, /*main_vals=*/true, dmask.dev,
+                     dvals.dev, dvecs.dev, s);
+        dvals.download();
+        dvecs.download();
+        if (dvals.staged() || dvecs.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_c_eig_aux_2d(const double *flowmap_aux, int64_t nx, int64_t ny, int n_aux, double dx, double dy,
+                        double h, int eig_main, const uint8_t *mask, double *eigvals, double *eigvecs,
+                        void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmap_aux && eigvals && eigvecs, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE(n_aux == 4 || n_aux == 5, "n_aux must be 4 or 5 (got %d)", n_aux);
+        B2_REQUIRE(!eig_main || n_aux == 5, "eig_main needs the centre point (n_aux = 5)");
+        B2_REQUIRE(h != 0.0 && dx != 0.0 && dy != 0.0, "h, dx and dy must be non-zero");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfa(flowmap_aux, np * n_aux * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dvals(eigvals, np * 2, s), dvecs(eigvecs, np * 4, s);
+        launch_c_eig(dfa.dev, nx, ny, n_aux, h, dx, dy, /*aux_vecs=*/true, /*main_vals=*/eig_main != 0,
+                     dmask.dev, dvals.dev, dvecs.dev, s);
+        dvals.download();
+        dvecs.download();
+        if (dvals.staged() || dvecs.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_ftle_from_eig(const double *eigval_max, int64_t n, int64_t stride, double T, double *ftle,
+                         void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(eigval_max && ftle, "null argument");
+        B2_REQUIRE(n >= 0 && stride >= 1, "bad size / stride");
+        B2_REQUIRE(T != 0.0, "T must be non-zero");
+        if (n == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> din(eigval_max, (size_t)(n - 1) * stride + 1, s);
+        Out<double> dout(ftle, n, s);
+        launch_ftle_from_eig(din.dev, n, stride, T, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
+                          int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
+                          double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
+                          double *pts_compact, int64_t capacity, int64_t *count, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(ftle && eigvec_max && x && y, "null argument");
+        B2_REQUIRE(nx >= 2 && ny >= 2, "the grid needs at least 2 points per axis");
+        B2_REQUIRE(ev_pixel_stride >= 1 && ev_comp_stride >= 1, "bad eigenvector strides");
+        B2_REQUIRE(!pts_compact || count, "pts_compact needs count");
+        B2_REQUIRE(capacity >= 0, "negative capacity");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> df(ftle, np, s);
+        In<double> dev(eigvec_max, (np - 1) * ev_pixel_stride + ev_comp_stride + 1, s);
+        // dx = x[1] - x[0], dy = y[1] - y[0] (ridges.py:39-40) are taken on the host
+        double x01[2], y01[2];
+        B2_CHECK_CUDA(cudaMemcpy(x01, x, sizeof(x01), cudaMemcpyDefault));
+        B2_CHECK_CUDA(cudaMemcpy(y01, y, sizeof(y01), cudaMemcpyDefault));
+        In<double> dxs(x, nx, s), dys(y, ny, s);
+        Out<double> drp(r_pts, np * 3, s), drv(r_vec, np * 2, s), dsdd(sdd, np, s);
+        // compact output: a host buffer only receives the rows that were found
+        Scratch cp_tmp, cnt_tmp;
+        double *cp_dev = pts_compact;
+        const bool cp_host = pts_compact && !is_device_ptr(pts_compact);
+        if (cp_host && capacity > 0) {
+            cp_tmp = Scratch((size_t)capacity * 2 * sizeof(double), s);
+            cp_dev = static_cast<double *>(cp_tmp.ptr);
+        }
+        long long *cnt_dev = nullptr;
+        const bool cnt_host = count && !is_device_ptr(count);
+        if (count) {
+            if (cnt_host) {
+                cnt_tmp = Scratch(sizeof(long long), s);
+                cnt_dev = static_cast<long long *>(cnt_tmp.ptr);
+            } else {
+                cnt_dev = reinterpret_cast<long long *>(count);
+            }
+        }
+        launch_ridge_pts(df.dev, dev.dev, ev_pixel_stride, ev_comp_stride, nx, ny, dxs.dev, dys.dev,
+                         x01[1] - x01[0], y01[1] - y01[0], sdd_thresh, f_min, drp.dev, drv.dev, dsdd.dev,
+                         capacity > 0 ? cp_dev : nullptr, capacity, cnt_dev, s);
+        drp.download();
+        drv.download();
+        dsdd.download();
+        if (cnt_host || cp_host) {
+            long long found = 0;
+            B2_CHECK_CUDA(cudaMemcpyAsync(&found, cnt_dev, sizeof(found), cudaMemcpyDeviceToHost, s));
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (cnt_host) *count = found;
+            const long long rows = found < capacity ? found : capacity;
+            if (cp_host && rows > 0)
+                B2_CHECK_CUDA(cudaMemcpyAsync(pts_compact, cp_dev, (size_t)rows * 2 * sizeof(double),
+                                              cudaMemcpyDeviceToHost, s));
+        }
+        if (drp.staged() || drv.staged() || dsdd.staged() || cp_host)
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(data && out2, "null argument");
+        B2_REQUIRE(n >= 1 && k >= 0 && k < n, "need 0 <= k < n (k = %lld, n = %lld)", (long long)k, (long long)n);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> din(data, n, s);
+        Out<double> dout(out2, 2, s);
+        launch_order_stats(din.dev, n, k, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

@@ -59,19 +59,32 @@ __device__ __forceinline__ double trig_reduce(double x, int &q) {
     q = __double2loint(t);
     const double k = t - kTrig.magic;
     double r = fma(-k, kTrig.p1, x);
+#ifdef B200CS_CW3
     r = fma(-k, kTrig.p2, r);
     return fma(-k, kTrig.p3, r);
+#else
+    // two Cody-Waite terms: p1 + p2 carries pi/2 to 107 bits, so the dropped k*p3 (< 1e-26 for
+    // |k| < 1e5) only matters when r itself is below ~1e-10, i.e. within rounding of a zero of
+    // sin/cos, where it changes the result by a few ulps of an O(1e-16) number
+    return fma(-k, kTrig.p2, r);
+#endif
 }
 
 // s[m] = sin(x[m] + shift * pi/2) for M independent arguments (shift = 1 gives cos).  ONE
 // polynomial per argument: its coefficients are picked by the quadrant parity through an indexed
 // constant-bank load (at most two distinct addresses per warp), so there is no branch, no
 // divergence and no second code copy.
+// |x| < 1e5 as an integer compare on the high word (1e5 = 0x40F86A00'00000000; false for NaN / inf):
+// keeps the range check off the FP64 pipe, which is the kernel's bottleneck
+__device__ __forceinline__ bool trig_in_range(double x) {
+    return (unsigned)(__double2hiint(x) & 0x7fffffff) < 0x40F86A00u;
+}
+
 template <int M, int SHIFT = 0>
 __device__ __forceinline__ void sin_v(const double (&x)[M], double (&s)[M]) {
     bool slow = false;
 #pragma unroll
-    for (int m = 0; m < M; ++m) slow |= !(fabs(x[m]) < 1.0e5);  // also catches NaN / inf
+    for (int m = 0; m < M; ++m) slow |= !trig_in_range(x[m]);  // also catches NaN / inf
     if (slow) {
 #pragma unroll
         for (int m = 0; m < M; ++m) {
@@ -102,6 +115,44 @@ __device__ __forceinline__ void sin_v(const double (&x)[M], double (&s)[M]) {
     }
 }
 
+// s[m] = sin(pi * u[m]).  The reduction is exact: k = rint(2u), r = u - k/2 with |r| <= 1/4 is
+// representable (a difference of nearby doubles), so the only rounding before the polynomial is
+// the single product pi*r -- three FP64 instructions fewer than forming pi*u and reducing it by
+// pi/2 in three Cody-Waite steps, and a smaller absolute error (no rounding of pi*u at |pi*u| ~ 6).
+template <int M>
+__device__ __forceinline__ void sinpi_v(const double (&u)[M], double (&s)[M]) {
+    bool slow = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) slow |= !trig_in_range(u[m]);
+    if (slow) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) s[m] = sincos_slow(3.141592653589793 * u[m]).x;
+        return;
+    }
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = fma(u[m], 2.0, kTrig.magic);
+        q[m] = __double2loint(t);
+        const double k = t - kTrig.magic;
+        r[m] = fma(k, -0.5, u[m]) * 3.141592653589793;
+        z[m] = r[m] * r[m];
+        p[m] = kTrig.sc[5][q[m] & 1];
+    }
+#pragma unroll
+    for (int k = 4; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kTrig.sc[k][q[m] & 1]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const bool par = q[m] & 1;
+        const double mm = z[m] * (par ? z[m] : r[m]);
+        const double base = par ? fma(z[m], -0.5, 1.0) : r[m];
+        s[m] = flip_sign(fma(mm, p[m], base), (q[m] >> 1) & 1);
+    }
+}
+
 __device__ __forceinline__ double sin_fast(double x) {
     const double a[1] = {x};
     double s[1];
@@ -118,7 +169,7 @@ __device__ __forceinline__ double cos_fast(double x) {
 
 // both outputs for one argument (both kernels are needed anyway)
 __device__ __forceinline__ void sincos_fast(double x, double *s, double *c) {
-    if (!(fabs(x) < 1.0e5)) {
+    if (!trig_in_range(x)) {
         const double2 sc = sincos_slow(x);
         *s = sc.x;
         *c = sc.y;

@@ -3,8 +3,8 @@
 
 namespace b200cs {
 
-void launch_flowmap_abc(const IntegArgs &A, bool grid_mode, cudaStream_t s) {
-    B2_REQUIRE(!grid_mode, "abc is a 3-D flow: use the point-list entry (flowmap / flowmap_n)");
+void launch_flowmap_abc(const IntegArgs &A, int mode, cudaStream_t s) {
+    B2_REQUIRE(!mode, "abc is a 3-D flow: use the point-list entry (flowmap / flowmap_n)");
     launch_rhs<Abc>(A, false, s);
 }
 

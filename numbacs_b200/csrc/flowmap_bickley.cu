@@ -3,7 +3,7 @@
 
 namespace b200cs {
 
-void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s) { launch_rhs<BickleyJet>(A, grid_mode, s); }
+void launch_flowmap_bickley(const IntegArgs &A, int mode, cudaStream_t s) { launch_rhs<BickleyJet>(A, mode, s); }
 
 void launch_lavd_bickley(const IntegArgs &A, cudaStream_t s) { launch_lavd_one<BickleyJet>(A, s); }
 

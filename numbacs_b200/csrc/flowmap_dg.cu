@@ -3,7 +3,7 @@
 
 namespace b200cs {
 
-void launch_flowmap_dg(const IntegArgs &A, bool grid_mode, cudaStream_t s) { launch_rhs<DoubleGyre>(A, grid_mode, s); }
+void launch_flowmap_dg(const IntegArgs &A, int mode, cudaStream_t s) { launch_rhs<DoubleGyre>(A, mode, s); }
 
 void launch_lavd_dg(const IntegArgs &A, cudaStream_t s) { launch_lavd_one<DoubleGyre>(A, s); }
 

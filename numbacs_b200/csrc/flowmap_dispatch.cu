@@ -5,10 +5,10 @@
 
 namespace b200cs {
 
-void launch_flowmap_dg(const IntegArgs &A, bool grid_mode, cudaStream_t s);
-void launch_flowmap_bickley(const IntegArgs &A, bool grid_mode, cudaStream_t s);
-void launch_flowmap_abc(const IntegArgs &A, bool grid_mode, cudaStream_t s);
-void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_flowmap_dg(const IntegArgs &A, int mode, cudaStream_t s);
+void launch_flowmap_bickley(const IntegArgs &A, int mode, cudaStream_t s);
+void launch_flowmap_abc(const IntegArgs &A, int mode, cudaStream_t s);
+void launch_flowmap_spline(int spherical, const IntegArgs &A, int mode, cudaStream_t s);
 void launch_lavd_dg(const IntegArgs &A, cudaStream_t s);
 void launch_lavd_bickley(const IntegArgs &A, cudaStream_t s);
 void launch_lavd_spline(int spherical, const IntegArgs &A, cudaStream_t s);
@@ -24,15 +24,15 @@ void launch_lavd_flowmap(const FlowSpec &f, const IntegArgs &A, cudaStream_t s) 
     }
 }
 
-void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s) {
+void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode, cudaStream_t s) {
     switch (f.kind) {
-    case B200CS_FLOW_DOUBLE_GYRE: launch_flowmap_dg(A, grid_mode, s); break;
-    case B200CS_FLOW_BICKLEY_JET: launch_flowmap_bickley(A, grid_mode, s); break;
+    case B200CS_FLOW_DOUBLE_GYRE: launch_flowmap_dg(A, mode, s); break;
+    case B200CS_FLOW_BICKLEY_JET: launch_flowmap_bickley(A, mode, s); break;
     case B200CS_FLOW_ABC:
-        launch_flowmap_abc(A, grid_mode, s);
+        launch_flowmap_abc(A, mode, s);
         break;
     case B200CS_FLOW_SPLINE2D:
-        launch_flowmap_spline(f.spherical, A, grid_mode, s);
+        launch_flowmap_spline(f.spherical, A, mode, s);
         break;
     default:
         set_error("handle is not a flow (kind %d)", f.kind);

@@ -56,7 +56,14 @@ struct RowSink {
     }
 };
 
-template <class Rhs, bool DENSE, bool GRID>
+// MODE: kModePts = point list pts[npts, N]; kModeGrid = 'ij' grid (x[i], y[j]);
+// kModeAux = auxiliary stencil of flowmap_aux_grid_2D (integration.py:249-464): particle
+// q = (i*ny + j)*n_aux + k starts at (x[i], y[j]) + aux_grid[k], aux_grid = [(h,0), (-h,0), (0,h),
+// (0,-h), (0,0)]; the n_aux stencil points of a cell are neighbouring lanes (their trajectories
+// and step sequences are practically identical, so they do not diverge).
+constexpr int kModePts = 0, kModeGrid = 1, kModeAux = 2;
+
+template <class Rhs, bool DENSE, int MODE>
 __global__ void __launch_bounds__(KernelShape<Rhs, DENSE>::kThreads, KernelShape<Rhs, DENSE>::kMinBlocks)
 flowmap_kernel(const __grid_constant__ IntegArgs A) {
     constexpr int N = Rhs::N;
@@ -65,13 +72,30 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
     const long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
     const bool in_range = q < A.npts;
     bool active = in_range;
-    if (active && A.mask != nullptr) active = (A.mask[q] == 0);
+    if (MODE != kModeAux && active && A.mask != nullptr) active = (A.mask[q] == 0);
 
     double y[N];
 #pragma unroll
     for (int i = 0; i < N; ++i) y[i] = 0.0;
-    if (active) {
-        if (GRID) {
+    if (MODE == kModeAux) {
+        if (active) {
+            const long long cell = q / A.n_aux;
+            const int k = (int)(q - cell * A.n_aux);
+            const long long i = cell / A.ny, j = cell - i * A.ny;
+            if (A.mask != nullptr) active = (A.mask[cell] == 0);
+            // edge cells: nothing without compute_edge; with it all four points when there is no
+            // centre point (n_aux == 4), else the centre point only (integration.py:320-343, 425-446)
+            if (i == 0 || i == A.nx - 1 || j == 0 || j == A.ny - 1)
+                active = active && A.aux_edge && (A.n_aux == 4 || k == 4);
+            if (active) {
+                const double ox = (k == 0) ? A.aux_h : (k == 1) ? -A.aux_h : 0.0;
+                const double oy = (k == 2) ? A.aux_h : (k == 3) ? -A.aux_h : 0.0;
+                y[0] = A.x[i] + ox;  // np.array([x[i], y[j]]) + aux_grid[k, :]
+                y[1] = A.y[j] + oy;
+            }
+        }
+    } else if (active) {
+        if (MODE == kModeGrid) {
             const long long i = q / A.ny, j = q - i * A.ny;
             y[0] = A.x[i];
             y[1] = A.y[j];
@@ -224,25 +248,32 @@ void launch_lavd_one(const IntegArgs &A, cudaStream_t s) {
     B2_CHECK_CUDA(cudaGetLastError());
 }
 
-template <class Rhs, bool DENSE, bool GRID>
+template <class Rhs, bool DENSE, int MODE>
 void launch_one(const IntegArgs &A, cudaStream_t s) {
     constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
     const long long blocks = (A.npts + kBlock - 1) / kBlock;
     if (blocks <= 0) return;
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
-    flowmap_kernel<Rhs, DENSE, GRID><<<(unsigned)blocks, kBlock, 0, s>>>(A);
+    flowmap_kernel<Rhs, DENSE, MODE><<<(unsigned)blocks, kBlock, 0, s>>>(A);
     B2_CHECK_CUDA(cudaGetLastError());
 }
 
 template <class Rhs>
-void launch_rhs(const IntegArgs &A, bool grid_mode, cudaStream_t s) {
+void launch_rhs(const IntegArgs &A, int mode, cudaStream_t s) {
     const bool dense = A.n_out >= 2;
-    if (dense) {
-        if (grid_mode) launch_one<Rhs, true, true>(A, s);
-        else launch_one<Rhs, true, false>(A, s);
+    if (mode == kModeAux) {
+        if constexpr (Rhs::N == 2) {
+            B2_REQUIRE(!dense, "the aux-grid flow map is a final-time quantity");
+            launch_one<Rhs, false, kModeAux>(A, s);
+        } else {
+            B2_REQUIRE(false, "the aux grid needs a 2-D flow");
+        }
+    } else if (dense) {
+        if (mode == kModeGrid) launch_one<Rhs, true, kModeGrid>(A, s);
+        else launch_one<Rhs, true, kModePts>(A, s);
     } else {
-        if (grid_mode) launch_one<Rhs, false, true>(A, s);
-        else launch_one<Rhs, false, false>(A, s);
+        if (mode == kModeGrid) launch_one<Rhs, false, kModeGrid>(A, s);
+        else launch_one<Rhs, false, kModePts>(A, s);
     }
 }
 

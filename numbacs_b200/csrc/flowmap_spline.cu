@@ -3,10 +3,10 @@
 
 namespace b200cs {
 
-void launch_flowmap_spline(int spherical, const IntegArgs &A, bool grid_mode, cudaStream_t s) {
-    if (spherical == 1) launch_rhs<Spline2D<1>>(A, grid_mode, s);
-    else if (spherical == 2) launch_rhs<Spline2D<2>>(A, grid_mode, s);
-    else launch_rhs<Spline2D<0>>(A, grid_mode, s);
+void launch_flowmap_spline(int spherical, const IntegArgs &A, int mode, cudaStream_t s) {
+    if (spherical == 1) launch_rhs<Spline2D<1>>(A, mode, s);
+    else if (spherical == 2) launch_rhs<Spline2D<2>>(A, mode, s);
+    else launch_rhs<Spline2D<0>>(A, mode, s);
 }
 
 void launch_lavd_spline(int spherical, const IntegArgs &A, cudaStream_t s) {

@@ -67,9 +67,14 @@ struct DoubleGyre {
         const double b = 1.0 - 2.0 * a;
         const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
         const double df = fma(2.0 * a, y[0], b);
-        const double arg[2] = {kPi * (f + y[1]), kPi * (f - y[1])};
         double s[2];
+#ifdef B200CS_DG_NO_SINPI
+        const double arg[2] = {kPi * (f + y[1]), kPi * (f - y[1])};
         sin_v<2>(arg, s);
+#else
+        const double arg[2] = {f + y[1], f - y[1]};
+        sinpi_v<2>(arg, s);  // sin(pi (f +- y)) with an exact argument reduction
+#endif
         if (damp != 0.0) {
             dy[0] = fma(-c, s[0] + s[1], damp * y[0]);
             dy[1] = fma(c * (s[0] - s[1]), df, damp * y[1]);

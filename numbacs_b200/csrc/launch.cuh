@@ -21,6 +21,9 @@ struct IntegArgs {
     const double *pts;
     long long npts;
     const uint8_t *mask;
+    // auxiliary stencil (flowmap_aux_grid_2D): n_aux = 4 or 5 particles per grid cell, offset h
+    int n_aux, aux_edge;
+    double aux_h;
     double *out;
     int *status;
     int *steps;
@@ -34,7 +37,7 @@ struct IntegArgs {
     double *lavd;              // [npts]
 };
 
-void launch_flowmap(const FlowSpec &f, const IntegArgs &A, bool grid_mode, cudaStream_t s);
+void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode /*0 pts, 1 grid, 2 aux grid*/, cudaStream_t s);
 void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, const double *y,
                      long long npts, double *dy, cudaStream_t s);
 
@@ -59,5 +62,21 @@ void launch_prefilter3(const double *data, long long n0, long long n1, long long
 void launch_div_scalar(double *a, long long n, double d, cudaStream_t s);
 void launch_interleave(const double *u, const double *v, long long count, double2 *uv, cudaStream_t s);
 void run_fp64_peak(int iters, double *tflops, double *ms);
+
+// ---- tensor_kernels.cu: Cauchy-Green tensor / eigen-pairs, ridge points, order statistics
+void launch_c_tensor(const double *fm_aux, long long nx, long long ny, int n_aux, double h,
+                     const uint8_t *mask, double *C, cudaStream_t s);
+// eigvals from the main-grid stencil (main_vals) or the aux stencil; eigvecs from the aux stencil
+// (aux_vecs) or the main grid.  fm is [nx, ny, n_aux, 2] (n_aux = 1: a plain flow map).
+void launch_c_eig(const double *fm, long long nx, long long ny, int n_aux, double h, double dx, double dy,
+                  bool aux_vecs, bool main_vals, const uint8_t *mask, double *eigvals, double *eigvecs,
+                  cudaStream_t s);
+void launch_ftle_from_eig(const double *eigval_max, long long n, long long stride, double T, double *ftle,
+                          cudaStream_t s);
+void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stride, long long ev_comp_stride,
+                      long long nx, long long ny, const double *x, const double *y, double dx, double dy,
+                      double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
+                      double *pts_compact, long long capacity, long long *count, cudaStream_t s);
+void launch_order_stats(const double *data, long long n, long long k, double *out2, cudaStream_t s);
 
 }  // namespace b200cs

@@ -4,6 +4,10 @@ ftle_grid_2D (diagnostics.py:21-65) and lavd_grid_2D (272-379) of the reference 
 arguments and layouts; both accept numpy arrays or torch CUDA tensors (then nothing crosses PCIe)
 and run as CUDA kernels of libb200cs.so.  flowmap_ftle_grid_2D is the fused convenience call for
 the README workflow (flow map + FTLE with the flow map kept on the device).
+
+C_tensor_2D (68-112), C_eig_aux_2D (115-197), C_eig_2D (200-244) and ftle_from_eig (247-269) feed
+the ridge / LCS extraction: eigenvalues ascending, eigenvectors as columns with np.linalg.eigh's
+(LAPACK's) sign conventions, bit-identical to the reference.
 """
 import ctypes as C
 
@@ -14,7 +18,7 @@ from .flows import ScalarField
 from .integration import _info_bufs, _fill_info, _method
 
 __all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D",
-           "lavd_flowmap_grid_2D"]
+           "lavd_flowmap_grid_2D", "C_tensor_2D", "C_eig_aux_2D", "C_eig_2D", "ftle_from_eig"]
 
 
 def ftle_grid_2D(flowmap, T, dx, dy, mask=None, *, device_out=False):
@@ -121,3 +125,66 @@ def lavd_flowmap_grid_2D(funcptr, t0, T, x, y, params, vort_interp, n=50, method
     if info is not None:
         info["status"], info["stats"] = status.obj, stats.obj
     return (lavd.obj, tspan, fm.obj) if return_flowmap else (lavd.obj, tspan)
+
+
+def _aux_in(flowmap_aux):
+    fa = _lib.arg_in(flowmap_aux)
+    if fa.obj.ndim != 4 or fa.obj.shape[3] != 2 or fa.obj.shape[2] not in (4, 5):
+        raise ValueError("flowmap_aux must have shape (nx, ny, 4 or 5, 2)")
+    return fa, int(fa.obj.shape[0]), int(fa.obj.shape[1]), int(fa.obj.shape[2])
+
+
+def C_tensor_2D(flowmap_aux, dx, dy, h=1e-5, mask=None, *, device_out=False):
+    """(C11, C12, C22) of the Cauchy-Green tensor from the aux-grid flow map -> (nx, ny, 3);
+    zero outside [2, nx-2) x [2, ny-2) and where masked.  dx, dy are unused, as in the reference."""
+    fa, nx, ny, n_aux = _aux_in(flowmap_aux)
+    ma = _lib.mask_in(mask)
+    dev = bool(device_out or fa.on_device)
+    out = _lib.alloc_out((nx, ny, 3), np.float64, dev)
+    _lib.check(_lib.load().b200cs_c_tensor_2d(fa.ptr, nx, ny, n_aux, float(dx), float(dy), float(h),
+                                              ma.ptr, out.ptr, _lib.current_stream(dev)))
+    return out.obj
+
+
+def C_eig_aux_2D(flowmap_aux, dx, dy, h=1e-5, eig_main=True, mask=None, *, device_out=False):
+    """Eigenvalues (nx, ny, 2) and eigenvectors (nx, ny, 2, 2) of the Cauchy-Green tensor from the
+    aux-grid flow map; with eig_main the eigenvalues come from the main-grid stencil."""
+    fa, nx, ny, n_aux = _aux_in(flowmap_aux)
+    if eig_main and n_aux != 5:
+        raise ValueError("eig_main=True needs flowmap_aux with the centre point (n_aux = 5)")
+    ma = _lib.mask_in(mask)
+    dev = bool(device_out or fa.on_device)
+    vals = _lib.alloc_out((nx, ny, 2), np.float64, dev)
+    vecs = _lib.alloc_out((nx, ny, 2, 2), np.float64, dev)
+    _lib.check(_lib.load().b200cs_c_eig_aux_2d(fa.ptr, nx, ny, n_aux, float(dx), float(dy), float(h),
+                                               int(bool(eig_main)), ma.ptr, vals.ptr, vecs.ptr,
+                                               _lib.current_stream(dev)))
+    return vals.obj, vecs.obj
+
+
+def C_eig_2D(flowmap, dx, dy, mask=None, *, device_out=False):
+    """Eigenvalues (nx, ny, 2) and eigenvectors (nx, ny, 2, 2) of the Cauchy-Green tensor from a
+    flow map (nx, ny, 2)."""
+    fm, ma = _lib.arg_in(flowmap), _lib.mask_in(mask)
+    if fm.obj.ndim != 3 or fm.obj.shape[2] != 2:
+        raise ValueError("flowmap must have shape (nx, ny, 2)")
+    nx, ny = int(fm.obj.shape[0]), int(fm.obj.shape[1])
+    dev = bool(device_out or fm.on_device)
+    vals = _lib.alloc_out((nx, ny, 2), np.float64, dev)
+    vecs = _lib.alloc_out((nx, ny, 2, 2), np.float64, dev)
+    _lib.check(_lib.load().b200cs_c_eig_2d(fm.ptr, nx, ny, float(dx), float(dy), ma.ptr, vals.ptr,
+                                           vecs.ptr, _lib.current_stream(dev)))
+    return vals.obj, vecs.obj
+
+
+def ftle_from_eig(eigval_max, T, *, device_out=False):
+    """FTLE from the largest Cauchy-Green eigenvalue: log(eigval_max) / (2|T|) where > 1, else 0.
+    A last-axis slice such as eigvals[:, :, 1] is read in place (strided)."""
+    e, stride = _lib.strided_in(eigval_max)
+    shape = tuple(int(v) for v in eigval_max.shape)
+    dev = bool(device_out or e.on_device)
+    out = _lib.alloc_out(shape, np.float64, dev)
+    n = int(np.prod(shape)) if shape else 1
+    _lib.check(_lib.load().b200cs_ftle_from_eig(e.ptr, n, stride, float(T), out.ptr,
+                                                _lib.current_stream(dev)))
+    return out.obj

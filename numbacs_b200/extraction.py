@@ -1,0 +1,110 @@
+"""FTLE ridge points -- drop-in for the data-parallel part of ``numbacs.extraction.ridges``.
+
+ftle_ridge_pts (extraction/ridges.py:9-76) and _ftle_ridge_pts_connect (232-318): the per-pixel
+sub-pixel ridge test (f > f_min, second directional derivative of f along the dominant
+Cauchy-Green eigenvector below -sdd_thresh, first-order root inside the pixel) as a CUDA stencil
+pass followed by an order-preserving stream compaction, so the points come back in the raveled
+pixel order of the reference's ``r_pts[ridge_bool, :]``.  ``np.percentile(f, percentile)`` becomes
+two order statistics found by a radix select on the device, combined with numba's interpolation
+formula (numba/np/arraymath.py: rank = 1 + (n-1) p/100, lower (1-m) + upper m).
+
+The serial linking of ridge points into curves (ridges.py:418-1054) is host-side geometry and is
+not part of this package.
+"""
+import ctypes as C
+from math import floor
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["ftle_ridge_pts", "percentile_value"]
+
+
+def percentile_value(f, percentile):
+    """np.percentile(f, percentile) as numba computes it, with the selection done on the GPU."""
+    fa = _lib.arg_in(f)
+    n = int(np.prod(fa.obj.shape))
+    if n == 0:
+        return float("nan")
+    p = float(percentile)
+    rank = 1 + (n - 1) * (p / 100.0)
+    fl = floor(rank)
+    m = rank - fl
+    k = min(max(int(fl) - 1, 0), n - 1)
+    out = np.empty(2, np.float64)
+    _lib.check(_lib.load().b200cs_order_stats(fa.ptr, n, k, C.c_void_p(out.ctypes.data),
+                                              _lib.current_stream(fa.on_device)))
+    if fa.on_device:
+        import torch
+        torch.cuda.current_stream().synchronize()
+    if p == 100:
+        return float(out[0])  # k = n - 1: the maximum
+    return float(out[0] * (1 - m) + out[1] * m)
+
+
+def _eigvec_in(eigvec_max, nx, ny):
+    """eigvec_max (nx, ny, 2), typically the view eigvecs[:, :, :, 1] of C_eig_2D's output: passed
+    in place with (pixel, component) strides when its layout allows it."""
+    is_t = _lib._is_torch(eigvec_max)
+    a = eigvec_max if is_t else np.asarray(eigvec_max)
+    if tuple(int(v) for v in a.shape) != (nx, ny, 2):
+        raise ValueError(f"eigvec_max must have shape {(nx, ny, 2)}")
+    f64 = (str(a.dtype) == "torch.float64") if is_t else (a.dtype == np.float64)
+    if f64:
+        si, sj, sc = _lib._elem_strides(a)
+        if sj >= 1 and sc >= 1 and si == sj * ny:
+            ptr = a.data_ptr() if is_t else a.ctypes.data
+            return _lib.Arg(a, C.c_void_p(ptr), bool(is_t and a.is_cuda)), sj, sc
+    return _lib.arg_in(a), 2, 1
+
+
+def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
+    fa, xa, ya = _lib.arg_in(f), _lib.arg_in(x), _lib.arg_in(y)
+    if fa.obj.ndim != 2:
+        raise ValueError("f must have shape (nx, ny)")
+    nx, ny = int(fa.obj.shape[0]), int(fa.obj.shape[1])
+    if nx < 2 or ny < 2:
+        raise ValueError("the grid needs at least 2 points per axis")
+    ev, ps, cs = _eigvec_in(eigvec_max, nx, ny)
+    f_min = 0.0 if percentile == 0 else percentile_value(fa.obj, percentile)
+    dev = bool(device_out or fa.on_device)
+    L = _lib.load()
+    stream = _lib.current_stream(dev)
+    count = np.zeros(1, np.int64)
+    cptr = C.c_void_p(count.ctypes.data)
+    if full:
+        r_pts = _lib.alloc_out((nx * ny, 3), np.float64, dev)
+        r_vec = _lib.alloc_out((nx * ny, 2), np.float64, dev)
+        sdd = _lib.alloc_out((nx * ny,), np.float64, dev)
+        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+                                           float(sdd_thresh), f_min, r_pts.ptr, r_vec.ptr, sdd.ptr,
+                                           None, 0, None, stream))
+        return r_pts.obj, r_vec.obj, sdd.obj
+    # one call = detect + scan + compact into a buffer sized by a guess (ridges are curves: their
+    # points are a small fraction of the pixels); only if the guess was too small, a second call
+    cap = max(4096, (nx * ny) // 32)
+    for _ in range(2):
+        pts = _lib.alloc_out((cap, 2), np.float64, dev)
+        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+                                           float(sdd_thresh), f_min, None, None, None, pts.ptr, cap,
+                                           cptr, stream))
+        n = int(count[0])
+        if n <= cap:
+            break
+        cap = n
+    return pts.obj[:n].clone() if dev else pts.obj[:n].copy()
+
+
+def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *, device_out=False):
+    """Sub-pixel FTLE ridge points -> (k, 2), in raveled pixel order."""
+    return _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, False, device_out)
+
+
+def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *, device_out=False):
+    """Per-pixel ridge data for the linking stage -> (r_pts (nx*ny, 3), r_vec (nx*ny, 2),
+    sdd (nx*ny,), h = min(dx, dy))."""
+    r_pts, r_vec, sdd = _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, True, device_out)
+    xs, ys = _lib.arg_in(x).obj, _lib.arg_in(y).obj
+    h = min(float(xs[1] - xs[0]), float(ys[1] - ys[0]))
+    return r_pts, r_vec, sdd, h

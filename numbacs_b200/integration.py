@@ -1,7 +1,7 @@
 """Particle integration -- drop-in for the hot-path part of ``numbacs.integration``.
 
-flowmap (integration.py:7), flowmap_n (64), flowmap_grid_2D (123), flowmap_n_grid_2D (467) of the
-reference, same positional arguments, defaults (method="dop853", rtol=1e-6, atol=1e-8, mask=None)
+flowmap (integration.py:7), flowmap_n (64), flowmap_grid_2D (123), flowmap_aux_grid_2D (249),
+flowmap_n_grid_2D (467) of the reference, same positional arguments, defaults (method="dop853", rtol=1e-6, atol=1e-8, mask=None)
 and output layouts ('ij' indexing, float64, zeros where masked).  The work is done by the
 one-thread-per-particle DOP853 kernels of libb200cs.so; ``funcptr`` must be a handle from
 ``numbacs_b200.flows``.
@@ -20,7 +20,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D"]
+__all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D"]
 
 
 def _method(method):
@@ -108,3 +108,25 @@ def flowmap_n_grid_2D(funcptr, t0, T, x, y, params, n=50, method="dop853", rtol=
                       mask=None, *, device_out=False, info=None):
     """Flow map at n equally spaced times over the grid -> ((nx, ny, n, 2), t_eval[n])."""
     return _grid(funcptr, t0, T, x, y, params, n, method, rtol, atol, mask, device_out, info)
+
+
+def flowmap_aux_grid_2D(funcptr, t0, T, x, y, params, h=1e-5, eig_main=True, compute_edge=True,
+                        method="dop853", rtol=1e-6, atol=1e-8, mask=None, *, device_out=False,
+                        info=None):
+    """Flow map at the final time over the auxiliary grid (x, y) +- h -> (nx, ny, n_aux, 2) with
+    n_aux = 5 (eig_main: the grid point itself is the last entry) or 4.  Entries the reference
+    leaves untouched (masked cells, the stencil points of edge cells) are 0."""
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
+    nx, ny = int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    if ma.obj is not None and tuple(ma.obj.shape) != (nx, ny):
+        raise ValueError(f"mask must have shape {(nx, ny)}")
+    n_aux = 5 if eig_main else 4
+    dev = bool(device_out or xa.on_device or ya.on_device or ma.on_device)
+    out = _lib.alloc_out((nx, ny, n_aux, 2), np.float64, dev)
+    status, steps, stats = _info_bufs(info, (nx, ny, n_aux), dev)
+    _lib.check(_lib.load().b200cs_flowmap_aux_grid_2d(
+        int(funcptr), float(t0), float(T), xa.ptr, nx, ya.ptr, ny, pa.ptr, int(pa.obj.shape[0]),
+        float(h), int(bool(eig_main)), int(bool(compute_edge)), _method(method), float(rtol),
+        float(atol), ma.ptr, out.ptr, status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
+    _fill_info(info, status, steps, stats)
+    return out.obj

@@ -7,6 +7,13 @@ rejected) step counts equal the oracle's -- DOP853's accept/reject decisions are
 a particle whose decision flips differs at the solver's truncation level (~1e-5) no matter how
 close the arithmetic is -- and the number of such particles is gated separately.
 
+Wall particles of the double gyre are the one systematic source of differing step sequences: the
+reference evaluates sin(fl(pi*2)) = -2.4e-16 there (a rounding artefact of pi*x), so its "zero"
+wall-normal velocity is 1e-17 noise that feeds hinit's h = 0.01*|y|/|f|, while the GPU's sin(pi u)
+with an exact argument reduction gives an exact 0.  Those particles do not move either way
+(|dx| ~ 1e-12), so the gates are stated on POSITIONS over all particles, with the step-sequence
+count kept as a bounded diagnostic.
+
 For strongly stretching cases (Bickley jet T = 6, spline fields) even a ONE-ULP change of one
 parameter moves some trajectories of the CPU oracle itself by far more than 1e-8 x L (measured:
 1.4e-5 at Bickley T = 6), because a noisy error estimate (err << 1) feeds the step-size formula.
@@ -55,7 +62,7 @@ def compare_flowmaps(gpu, info, ora, steps_o, L):
     """-> dict with mismatch count and error statistics relative to the domain size L."""
     d = (np.abs(gpu - ora) / np.asarray(L)).max(axis=-1)
     same = (np.asarray(info["steps"]) == steps_o).all(axis=-1)
-    return {"n": d.size, "mismatch": int((~same).sum()),
+    return {"n": d.size, "mismatch": int((~same).sum()), "n_bad": int((d > 1e-8).sum()),
             "max_match": float(d[same].max()) if same.any() else 0.0,
             "max_all": float(d.max()), "p99": float(np.percentile(d, 99)),
             "median": float(np.median(d))}
@@ -221,8 +228,8 @@ def test_double_gyre_C1(nb, oracle):
     fmo, _, st_o, steps_o, stats_o = oracle.flowmap_grid_2D(fo, 0.0, -10.0, x, y, po, full=True)
     r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
     assert (info["status"] == 1).all() and (st_o == 1).all()
-    assert r["mismatch"] <= max(1, int(1e-6 * r["n"]) + 1), r
-    assert r["max_match"] <= 1e-8, r                      # north_star: 1e-8 x domain size
+    assert r["max_all"] <= 1e-8, r                        # north_star: 1e-8 x domain size, EVERY particle
+    assert r["mismatch"] <= 4, r                          # at most the stationary corner particles
     if r["mismatch"] == 0:
         assert np.array_equal(info["stats"], stats_o)     # same nfev / accepted / rejected totals
     # FTLE from both flow maps: relative L2 <= 1e-6
@@ -380,8 +387,11 @@ def test_flowmap_n_dense_output(nb, oracle):
     fmno, tso, _, steps_o, stats_o = oracle.flowmap_n_grid_2D(fo, 1.0, 9.0, x, y, po, full=True)
     assert fmn.shape == (64, 33, 50, 2) and np.array_equal(ts, tso)
     same = (info["steps"] == steps_o).all(axis=-1)
-    assert (~same).sum() <= 1
-    assert np.abs(fmn - fmno)[same].max() <= 1e-8
+    wall = np.zeros_like(same)
+    wall[[0, -1], :] = True
+    wall[:, [0, -1]] = True
+    assert (~same).sum() <= 4 and wall[~same].all()       # only stationary corner / wall particles
+    assert np.abs(fmn - fmno).max() <= 1e-8               # every particle, every output time
     if same.all():
         assert np.array_equal(info["stats"], stats_o)      # incl. the 3 extra RHS per dense step
     # backward with p0 = -1: tspan is the physical time (integration.py:533)

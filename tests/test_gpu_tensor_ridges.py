@@ -1,0 +1,218 @@
+"""GPU parity tests for the rows of SURVEY.md section 8(f) built so far: aux-grid flow map,
+Cauchy-Green tensor / eigen-pairs, ftle_from_eig, FTLE ridge points, order statistics -- all
+through the ctypes C-ABI of libb200cs.so, against the reference's goldens, the frozen outputs of
+the real reference code, and the CPU oracle.
+
+The tensor / eigen / ridge kernels use explicitly rounded arithmetic in the reference's operation
+order, so they are required to be BIT-IDENTICAL to the reference outputs (eigenvector signs
+included); the aux-grid flow map carries the usual solver tolerance (1e-8 x domain over particles
+with identical step sequences)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def apply_mask(arr, mask):
+    out = arr.copy()
+    out[mask] = 0.0
+    return out
+
+
+def reconstruct_matrix(evals, evecs):
+    return np.einsum("...ik,...k,...jk->...ij", evecs, evals, evecs)
+
+
+@pytest.fixture(scope="module")
+def nb(lib):
+    import numbacs_b200 as nb
+    from numbacs_b200 import _lib
+    assert _lib.device_count() >= 1
+    return nb
+
+
+# ------------------------------------------------------------------ flowmap_aux_grid_2D
+
+def test_flowmap_aux_golden(nb, golden, coords_dg, mask_dg):
+    """tests/test_integration.py:66-75 of the reference, on the GPU."""
+    x, y = coords_dg
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fa = nb.integration.flowmap_aux_grid_2D(f, 0.0, 8.0, x, y, p)
+    assert fa.shape == (21, 11, 5, 2) and fa.dtype == np.float64
+    assert np.array_equal(fa.astype(np.float32), golden["ref_fm_aux"])
+    assert np.array_equal(fa[:, :, 4, :], nb.integration.flowmap_grid_2D(f, 0.0, 8.0, x, y, p))
+    fa_m = nb.integration.flowmap_aux_grid_2D(f, 0.0, 8.0, x, y, p, mask=mask_dg)
+    assert np.array_equal(fa_m.astype(np.float32), apply_mask(golden["ref_fm_aux"], mask_dg))
+
+
+@pytest.mark.parametrize("eig_main,compute_edge", [(True, True), (True, False), (False, True), (False, False)])
+def test_flowmap_aux_vs_oracle(nb, oracle, eig_main, compute_edge):
+    x, y = np.linspace(0, 2, 61), np.linspace(0, 1, 37)
+    rng = np.random.default_rng(3)
+    mask = rng.random((61, 37)) < 0.1
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    fo, po, _ = oracle.get_predefined_flow("double_gyre", int_direction=-1.0)
+    info = {}
+    fa = nb.integration.flowmap_aux_grid_2D(f, 0.0, -10.0, x, y, p, h=1e-5, eig_main=eig_main,
+                                            compute_edge=compute_edge, mask=mask, info=info)
+    fao, status_o, steps_o, stats_o = oracle.flowmap_aux_grid_2D(
+        fo, 0.0, -10.0, x, y, po, h=1e-5, eig_main=eig_main, compute_edge=compute_edge, mask=mask,
+        full=True)
+    assert fa.shape == fao.shape
+    # exactly the same set of integrated entries, zeros elsewhere
+    assert np.array_equal(info["status"] == 1, status_o == 1)
+    assert not fa[status_o != 1].any()
+    same = (info["steps"] == steps_o).all(axis=-1)
+    assert (~same).sum() <= max(1, int(1e-4 * same.size))
+    d = (np.abs(fa - fao) / np.array([2.0, 1.0])).max(axis=-1)
+    assert d[same].max() <= 1e-8
+    assert tuple(info["stats"]) == tuple(stats_o) or (~same).any()
+
+
+# ------------------------------------------------------------------ tensor / eigen-pairs
+
+def test_tensor_goldens(nb, golden, coords_dg, mask_dg):
+    """tests/test_diagnostics.py:99-150 of the reference, on the GPU."""
+    x, y = coords_dg
+    D = nb.diagnostics
+    fa = golden["ref_fm_aux"].astype(np.float64)
+    fm = golden["ref_fm"].astype(np.float64)
+    C = D.C_tensor_2D(fa, x[1], y[1])
+    assert np.allclose(C.astype(np.float32), golden["ref_C"])
+    Cm = D.C_tensor_2D(fa, x[1], y[1], mask=mask_dg)
+    assert np.allclose(Cm.astype(np.float32), apply_mask(golden["ref_C"], mask_dg))
+    for fn, inp, gv, ge in ((D.C_eig_aux_2D, fa, "ref_Cevals_aux", "ref_Cevecs_aux"),
+                            (D.C_eig_2D, fm, "ref_Cevals", "ref_Cevecs")):
+        Cexp = reconstruct_matrix(golden[gv], golden[ge])
+        vals, vecs = fn(inp, x[1], y[1])
+        assert np.allclose(reconstruct_matrix(vals.astype(np.float32), vecs.astype(np.float32)), Cexp)
+        vals, vecs = fn(inp, x[1], y[1], mask=mask_dg)
+        assert np.allclose(reconstruct_matrix(vals.astype(np.float32), vecs.astype(np.float32)),
+                           apply_mask(Cexp, mask_dg))
+
+
+def test_tensor_functions_bit_identical_to_reference(nb, golden):
+    """Frozen outputs of the real numbacs.diagnostics code (numba + LAPACK eigh)."""
+    D = nb.diagnostics
+    dx, dy, h = golden["ceig_args"]
+    fm, fa, mask = golden["ceig_in"], golden["caux_in"], golden["ceig_mask"]
+    for tag, m in (("", None), ("_masked", mask)):
+        vals, vecs = D.C_eig_2D(fm, dx, dy, m)
+        assert np.array_equal(vals, golden["ceig_vals" + tag])
+        assert np.array_equal(vecs, golden["ceig_vecs" + tag])
+        assert np.array_equal(D.C_tensor_2D(fa, dx, dy, h, m), golden["ctensor" + tag])
+        vals, vecs = D.C_eig_aux_2D(fa, dx, dy, h, True, m)
+        assert np.array_equal(vals, golden["caux_vals_main" + tag])
+        assert np.array_equal(vecs, golden["caux_vecs_main" + tag])
+        vals, vecs = D.C_eig_aux_2D(np.ascontiguousarray(fa[:, :, :4]), dx, dy, h, False, m)
+        assert np.array_equal(vals, golden["caux_vals" + tag])
+        assert np.array_equal(vecs, golden["caux_vecs" + tag])
+    ft = D.ftle_from_eig(golden["ceig_vals"][:, :, 1], -3.0)        # strided view, read in place
+    assert ft.shape == golden["ftle_from_eig_out"].shape
+    assert np.allclose(ft, golden["ftle_from_eig_out"], rtol=1e-15, atol=0)
+    assert np.array_equal(ft == 0, golden["ftle_from_eig_out"] == 0)
+
+
+def test_eigh_degenerate_matrices(nb, oracle):
+    """Flow maps chosen so that the Cauchy-Green tensor is diagonal, a multiple of the identity,
+    zero, or has a negligible off-diagonal: the split branch of LAPACK's dsteqr."""
+    X, Y = np.meshgrid(np.linspace(0, 1, 9), np.linspace(0, 1, 7), indexing="ij")
+    cases = [np.stack([2 * X, 3 * Y], -1), np.stack([3 * X, 2 * Y], -1), np.stack([X, Y], -1),
+             np.zeros(X.shape + (2,)), np.stack([2 * X + 1e-17 * Y, 3 * Y], -1),
+             np.stack([X + 0.5 * Y, Y], -1), np.stack([Y, X], -1)]
+    for fm in cases:
+        vals, vecs = nb.diagnostics.C_eig_2D(fm, 0.125, 1 / 6)
+        vo, eo = oracle.C_eig_2D(fm, 0.125, 1 / 6)
+        assert np.array_equal(vals, vo) and np.array_equal(vecs, eo)
+
+
+def test_c_eig_matches_ftle_kernel_and_oracle_on_a_real_flow_map(nb, oracle):
+    x, y = np.linspace(0, 2, 301), np.linspace(0, 1, 151)
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x, y, p)
+    vals, vecs = nb.diagnostics.C_eig_2D(fm, dx, dy)
+    vo, eo = oracle.C_eig_2D(fm, dx, dy)
+    assert np.array_equal(vals, vo) and np.array_equal(vecs, eo)
+    # unit eigenvectors, C v = lambda v reconstructs the tensor
+    assert np.allclose(np.linalg.norm(vecs[1:-1, 1:-1], axis=2), 1.0, atol=1e-14)
+    ft_eig = nb.diagnostics.ftle_from_eig(vals[:, :, 1], -10.0)
+    ft = nb.diagnostics.ftle_grid_2D(fm, -10.0, dx, dy)
+    assert np.linalg.norm(ft_eig - ft) / np.linalg.norm(ft) <= 1e-9   # same field, two routes
+    assert np.allclose(ft_eig, oracle.ftle_from_eig(vo[:, :, 1], -10.0), rtol=1e-14, atol=0)
+    # torch tensors stay on the device
+    import torch
+    fmd = torch.from_numpy(fm).cuda()
+    vd, ed = nb.diagnostics.C_eig_2D(fmd, dx, dy)
+    assert vd.is_cuda and ed.is_cuda
+    assert np.array_equal(vd.cpu().numpy(), vals) and np.array_equal(ed.cpu().numpy(), vecs)
+    ftd = nb.diagnostics.ftle_from_eig(vd[:, :, 1], -10.0)
+    assert ftd.is_cuda and np.array_equal(ftd.cpu().numpy(), ft_eig)
+
+
+# ------------------------------------------------------------------ ridge points
+
+def test_ridge_pts_golden(nb, golden, coords_dg):
+    """tests/test_extraction.py:7-13 of the reference, on the GPU."""
+    x, y = coords_dg
+    r = nb.extraction.ftle_ridge_pts(golden["ref_ftle"], golden["ref_Cevecs"][:, :, :, 1], x, y)
+    assert r.shape == golden["ref_ridge_pts"].shape
+    assert np.allclose(r, golden["ref_ridge_pts"])
+
+
+def test_ridge_pts_bit_identical_to_reference(nb, golden):
+    """Frozen outputs of the real numbacs/extraction/ridges.py on a seeded float64 field, incl.
+    sdd_thresh and the percentile threshold (np.percentile as numba computes it)."""
+    from numbacs_b200.extraction import _ftle_ridge_pts_connect, percentile_value
+    f, ev, x, y = golden["ridge_f"], golden["ridge_ev"], golden["ridge_x"], golden["ridge_y"]
+    for tag, (thr, pct) in zip("abc", golden["ridge_args"]):
+        r = nb.extraction.ftle_ridge_pts(f, ev, x, y, thr, int(pct))
+        assert np.array_equal(r, golden["ridge_pts_" + tag])
+        rp, rv, sdd, h = _ftle_ridge_pts_connect(f, ev, x, y, thr, int(pct))
+        assert np.array_equal(rp, golden["ridge_conn_pts_" + tag])
+        assert np.array_equal(rv, golden["ridge_conn_vec_" + tag])
+        assert np.array_equal(sdd, golden["ridge_conn_sdd_" + tag])
+        assert h == min(x[1] - x[0], y[1] - y[0])
+    for pct in (1, 25, 50, 60, 99.5, 100):
+        assert percentile_value(f, pct) == np.percentile(f, pct) or \
+            abs(percentile_value(f, pct) - np.percentile(f, pct)) <= 1e-15 * abs(np.percentile(f, pct))
+
+
+def test_order_stats_against_sort(nb, lib):
+    import ctypes as C
+    rng = np.random.default_rng(11)
+    for data in (rng.normal(size=100003), np.round(rng.normal(size=50000), 1),     # many ties
+                 np.concatenate([np.zeros(3000), -np.zeros(10), rng.random(100)]),  # mostly zeros
+                 np.array([3.5]), -rng.random(777) * 1e-300, rng.normal(size=4096) * 1e300):
+        s = np.sort(data)
+        n = data.size
+        for k in sorted({0, n // 3, n // 2, n - 2, n - 1} & set(range(n))):
+            out = np.zeros(2)
+            rc = lib.b200cs_order_stats(C.c_void_p(data.ctypes.data), n, k,
+                                        C.c_void_p(out.ctypes.data), None)
+            assert rc == 0
+            assert out[0] == s[k] and out[1] == s[min(k + 1, n - 1)], (n, k, out, s[k])
+
+
+def test_ridge_pipeline_on_a_real_ftle_field(nb, oracle):
+    """Config 5's tail at a size the oracle finishes in seconds: flow map -> C_eig_2D ->
+    ftle_from_eig -> ridge points (plot_dg_ftle_ridges.py:43-72), device-resident end to end."""
+    import torch
+    x, y = np.linspace(0, 2, 401), np.linspace(0, 1, 201)
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, -10.0, x, y, p, device_out=True)
+    vals, vecs = nb.diagnostics.C_eig_2D(fm, dx, dy)
+    ftle = nb.diagnostics.ftle_from_eig(vals[:, :, 1], -10.0)
+    r = nb.extraction.ftle_ridge_pts(ftle, vecs[:, :, :, 1], x, y, sdd_thresh=10.0, percentile=50)
+    assert r.is_cuda and r.shape[1] == 2 and r.shape[0] > 100
+    # oracle on the same (GPU-produced) fields
+    ftle_h, vecs_h = ftle.cpu().numpy(), vecs.cpu().numpy()
+    ro = oracle.ftle_ridge_pts(ftle_h, vecs_h[:, :, :, 1], x, y, sdd_thresh=10.0, percentile=50)
+    assert np.array_equal(r.cpu().numpy(), ro)
+    # every ridge point lies within half a cell of a grid point with ftle above the median
+    rr = r.cpu().numpy()
+    i = np.rint(rr[:, 0] / dx).astype(int)
+    j = np.rint(rr[:, 1] / dy).astype(int)
+    assert (np.abs(rr[:, 0] - x[i]) <= dx / 2 + 1e-12).all() and (np.abs(rr[:, 1] - y[j]) <= dy / 2 + 1e-12).all()
+    assert (ftle_h[i, j] > np.percentile(ftle_h, 50)).all()
