@@ -21,6 +21,8 @@ A step = one full flow map + FTLE pass.
           statistics, divided by the kernel time measured live with CUDA events; peak = FP64 DFMA
           peak measured in this run (MEASURED_PEAKS.json has no FP64 entry).
   roofline_ftle : the FTLE stencil kernel against the measured HBM copy bandwidth (24 B/pixel).
+  ridge_tail    : config 5's "+ FTLE ridge extraction" (C_eig_2D -> ftle_from_eig -> ftle_ridge_pts on
+          the step's flow map), timed on its own after the K steps and reported beside the metric.
   cpu_baseline  : the CPU oracle (a port of the reference algorithm, oracle/) on all host threads
           over a bounded contiguous row sample of the same grid.
 
@@ -294,6 +296,37 @@ def run_b200(args):
     e2e_ms = e0.elapsed_time(e1)
     checksum = float(ftle_host.sum()) if rows else 0.0   # device->host result actually read
 
+    # ---- config 5's tail, reported beside the metric (not inside it): Cauchy-Green eigen-pairs ->
+    # FTLE from the largest eigenvalue -> sub-pixel ridge points, on the flow map of the last step
+    # (examples/ftle/plot_dg_ftle_ridges.py:43-72: percentile 0, sdd_thresh 10).  N = 1 only.
+    ridge = None
+    if world == 1 and not args.no_ridges:
+        from numbacs_b200.diagnostics import C_eig_2D, ftle_from_eig
+        from numbacs_b200.extraction import ftle_ridge_pts
+        fm_full = slab[has_lo:has_lo + rows]
+
+        def tail():
+            vals, vecs = C_eig_2D(fm_full, dx, dy)
+            ft2 = ftle_from_eig(vals[:, :, 1], TINT)
+            return ft2, ftle_ridge_pts(ft2, vecs[:, :, :, 1], x_dev, y_dev, sdd_thresh=10.0, percentile=0)
+
+        tail()
+        best = float("inf")
+        for _ in range(3):
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record(stream)
+            ft2, rp = tail()
+            r1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, r0.elapsed_time(r1))
+        ridge = {"ms": best, "n_ridge_pts": int(rp.shape[0]),
+                 "ftle_vs_ftle_grid_2D_rel_l2": float(torch.linalg.norm(ft2 - ftle) / torch.linalg.norm(ftle)),
+                 "kernels": "C_eig_2D + ftle_from_eig + ftle_ridge_pts (detect, scan, compact), device-timed, "
+                            "best of 3; sdd_thresh=10, percentile=0",
+                 "algorithmic_bytes_per_point": 64 + 16 + 2 * 24}
+        del ft2, rp
+        torch.cuda.empty_cache()
+
     # ---- max over ranks
     t = torch.tensor([span_ms, e2e_ms, fm_ms, ft_ms, halo_ms], dtype=torch.float64, device="cuda")
     agg = torch.cat([torch.tensor(st, dtype=torch.float64, device="cuda"),
@@ -367,6 +400,7 @@ def run_b200(args):
             "roofline_ftle": {"bound": "hbm", "achieved": ftle_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": ftle_gbs / hbm_peak, "traffic": ftle_traffic, "kernel": "ftle_kernel",
                               "kernel_ms": ft_ms, "peak_source": hbm_src, "bytes_per_point": 24},
+            "ridge_tail": ridge,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "halo_exchange_ms": halo_ms if world > 1 else 0.0,
@@ -389,6 +423,7 @@ def main():
     ap.add_argument("--n", type=int, default=16384, help="grid is n x n (BASELINE: 16384)")
     ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-ridges", action="store_true", help="skip the ridge-extraction tail (N = 1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -251,6 +251,17 @@ B200CS_API int b200cs_ftle_ridge_pts(const double *ftle /*[nx,ny]*/, const doubl
                           double *r_pts, double *r_vec, double *sdd, double *pts_compact,
                           int64_t capacity, int64_t *count, void *stream);
 
+/* ftle_ridges(f, eigvec_max, x, y, sdd_thresh, percentile, min_ridge_pts)   (ridges.py:79-229)
+ * The ridge points of b200cs_ftle_ridge_pts together with the 8-connected component of ridge
+ * pixels each belongs to: roots_compact[k] is the smallest raveled pixel index of point k's
+ * component (so ascending roots = scipy.ndimage.label's numbering, which the reference uses).
+ * Points come in raveled-pixel order; grouping them by root gives the reference's list of ridges. */
+B200CS_API int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
+                       int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
+                       double sdd_thresh, double f_min, double *pts_compact /*[capacity,2]*/,
+                       int64_t *roots_compact /*[capacity]*/, int64_t capacity, int64_t *count,
+                       void *stream);
+
 /* out2 = { sorted(data)[k], sorted(data)[min(k+1, n-1)] } by radix select (no sort, data is not
  * modified): the two order statistics np.percentile interpolates between (ridges.py:45, 279). */
 B200CS_API int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream);

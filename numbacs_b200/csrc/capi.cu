@@ -844,6 +844,62 @@ int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t 
     });
 }
 
+int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
+                       int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
+                       double sdd_thresh, double f_min, double *pts_compact, int64_t *roots_compact,
+                       int64_t capacity, int64_t *count, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(ftle && eigvec_max && x && y && count, "null argument");
+        B2_REQUIRE(nx >= 2 && ny >= 2, "the grid needs at least 2 points per axis");
+        B2_REQUIRE(ev_pixel_stride >= 1 && ev_comp_stride >= 1, "bad eigenvector strides");
+        B2_REQUIRE(capacity >= 0 && (capacity == 0 || (pts_compact && roots_compact)), "bad output buffers");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> df(ftle, np, s);
+        In<double> dev(eigvec_max, (np - 1) * ev_pixel_stride + ev_comp_stride + 1, s);
+        double x01[2], y01[2];
+        B2_CHECK_CUDA(cudaMemcpy(x01, x, sizeof(x01), cudaMemcpyDefault));
+        B2_CHECK_CUDA(cudaMemcpy(y01, y, sizeof(y01), cudaMemcpyDefault));
+        In<double> dxs(x, nx, s), dys(y, ny, s);
+        const bool host_out = capacity > 0 && !is_device_ptr(pts_compact);
+        B2_REQUIRE(capacity == 0 || host_out == !is_device_ptr(roots_compact),
+                   "pts_compact and roots_compact must both be host or both be device buffers");
+        Scratch cp_tmp, rt_tmp, cnt_tmp;
+        double *cp_dev = pts_compact;
+        long long *rt_dev = reinterpret_cast<long long *>(roots_compact);
+        if (host_out) {
+            cp_tmp = Scratch((size_t)capacity * 2 * sizeof(double), s);
+            rt_tmp = Scratch((size_t)capacity * sizeof(long long), s);
+            cp_dev = static_cast<double *>(cp_tmp.ptr);
+            rt_dev = static_cast<long long *>(rt_tmp.ptr);
+        }
+        const bool cnt_host = !is_device_ptr(count);
+        long long *cnt_dev = reinterpret_cast<long long *>(count);
+        if (cnt_host) {
+            cnt_tmp = Scratch(sizeof(long long), s);
+            cnt_dev = static_cast<long long *>(cnt_tmp.ptr);
+        }
+        launch_ridge_components(df.dev, dev.dev, ev_pixel_stride, ev_comp_stride, nx, ny, dxs.dev, dys.dev,
+                                x01[1] - x01[0], y01[1] - y01[0], sdd_thresh, f_min, cp_dev, rt_dev, capacity,
+                                cnt_dev, s);
+        if (cnt_host || host_out) {
+            long long found = 0;
+            B2_CHECK_CUDA(cudaMemcpyAsync(&found, cnt_dev, sizeof(found), cudaMemcpyDeviceToHost, s));
+            B2_CHECK_CUDA(cudaStreamSynchronize(s));
+            if (cnt_host) *count = found;
+            const long long rows = found < capacity ? found : capacity;
+            if (host_out && rows > 0) {
+                B2_CHECK_CUDA(cudaMemcpyAsync(pts_compact, cp_dev, (size_t)rows * 2 * sizeof(double),
+                                              cudaMemcpyDeviceToHost, s));
+                B2_CHECK_CUDA(cudaMemcpyAsync(roots_compact, rt_dev, (size_t)rows * sizeof(long long),
+                                              cudaMemcpyDeviceToHost, s));
+                B2_CHECK_CUDA(cudaStreamSynchronize(s));
+            }
+        }
+    });
+}
+
 int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream) {
     return guarded([&] {
         require_device();

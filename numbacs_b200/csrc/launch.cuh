@@ -77,6 +77,11 @@ void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stri
                       long long nx, long long ny, const double *x, const double *y, double dx, double dy,
                       double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
                       double *pts_compact, long long capacity, long long *count, cudaStream_t s);
+void launch_ridge_components(const double *f, const double *ev, long long ev_pixel_stride,
+                             long long ev_comp_stride, long long nx, long long ny, const double *x,
+                             const double *y, double dx, double dy, double sdd_thresh, double f_min,
+                             double *pts_compact, long long *roots_compact, long long capacity,
+                             long long *count, cudaStream_t s);
 void launch_order_stats(const double *data, long long n, long long k, double *out2, cudaStream_t s);
 
 }  // namespace b200cs

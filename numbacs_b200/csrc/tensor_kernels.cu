@@ -323,6 +323,89 @@ ridge_compact_kernel(const __grid_constant__ RidgeArgs R, const long long *__res
     }
 }
 
+// ---- connected ridges (ftle_ridges, ridges.py:175-229) ------------------------------------------
+// The reference labels the 8-connected components of ridge_bool with scipy.ndimage.label and then
+// gathers each component's points with one full-grid comparison per label.  Here: union-find over
+// the ridge pixels (every pixel links to its W / NW / N / NE ridge neighbours, roots are the
+// smallest raveled index of their component, so sorting roots reproduces scipy's raster-order
+// label numbering), then the same ordered compaction as above carrying each point's root.
+__global__ void __launch_bounds__(kTB)
+ridge_flag_kernel(const __grid_constant__ RidgeArgs R, int *__restrict__ parent, int *__restrict__ block_counts) {
+    const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
+    bool hit = false;
+    if (q < R.nx * R.ny) {
+        double px, py, ex, ey, c2;
+        hit = ridge_at(R, q, px, py, ex, ey, c2);
+        parent[q] = hit ? (int)q : -1;
+    }
+    const int cnt = __syncthreads_count(hit ? 1 : 0);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
+}
+
+// parent pointers only ever decrease and always stay inside the component, so a stale value is
+// still a valid ancestor; the loads go to L2 (where the atomics land) to keep the walks short
+__device__ __forceinline__ int uf_find(const int *parent, int x) {
+    int p = __ldcg(parent + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(parent + x);
+    }
+    return x;
+}
+
+__device__ __forceinline__ void uf_union(int *parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&parent[b], a);  // link the larger root under the smaller
+        if (old == b) return;
+        b = old;  // somebody re-rooted b meanwhile: merge what it points to now
+    }
+}
+
+__global__ void __launch_bounds__(kTB)
+ridge_merge_kernel(int *parent, long long nx, long long ny) {
+    const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
+    if (q >= nx * ny || parent[q] < 0) return;
+    const long long i = q / ny, j = q - i * ny;
+    if (j > 0 && parent[q - 1] >= 0) uf_union(parent, (int)q, (int)(q - 1));
+    if (i > 0) {
+        const long long u = q - ny;
+        if (parent[u] >= 0) uf_union(parent, (int)q, (int)u);
+        if (j > 0 && parent[u - 1] >= 0) uf_union(parent, (int)q, (int)(u - 1));
+        if (j < ny - 1 && parent[u + 1] >= 0) uf_union(parent, (int)q, (int)(u + 1));
+    }
+}
+
+__global__ void __launch_bounds__(kTB)
+ridge_compact_roots_kernel(const __grid_constant__ RidgeArgs R, const int *__restrict__ parent,
+                           const long long *__restrict__ offsets, double *__restrict__ pts,
+                           long long *__restrict__ roots, long long capacity) {
+    __shared__ int warp_cnt[kTB / 32];
+    const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
+    const bool hit = (q < R.nx * R.ny) && parent[q] >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, hit);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[wid] = __popc(bal);
+    __syncthreads();
+    if (!hit) return;
+    long long pos = offsets[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+    for (int w = 0; w < wid; ++w) pos += warp_cnt[w];
+    if (pos < capacity) {
+        double px, py, ex, ey, c2;
+        ridge_at(R, q, px, py, ex, ey, c2);
+        pts[2 * pos] = px;
+        pts[2 * pos + 1] = py;
+        roots[pos] = uf_find(parent, (int)q);
+    }
+}
+
 // ---- order statistics: sorted(data)[k] and sorted(data)[k+1] by MSB-first radix select ----------
 struct SelectState {
     unsigned long long prefix, mask;  // key bits fixed so far
@@ -444,10 +527,9 @@ void launch_ftle_from_eig(const double *eigval_max, long long n, long long strid
     B2_CHECK_CUDA(cudaGetLastError());
 }
 
-void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stride, long long ev_comp_stride,
-                      long long nx, long long ny, const double *x, const double *y, double dx, double dy,
-                      double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
-                      double *pts_compact, long long capacity, long long *count, cudaStream_t s) {
+static RidgeArgs make_ridge_args(const double *f, const double *ev, long long ev_pixel_stride,
+                                 long long ev_comp_stride, long long nx, long long ny, const double *x,
+                                 const double *y, double dx, double dy, double sdd_thresh, double f_min) {
     RidgeArgs R{};
     R.f = f;
     R.ev = ev;
@@ -466,6 +548,37 @@ void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stri
     R.half_dy = dy / 2;
     R.sdd_thresh = sdd_thresh;
     R.f_min = f_min;
+    return R;
+}
+
+void launch_ridge_components(const double *f, const double *ev, long long ev_pixel_stride,
+                             long long ev_comp_stride, long long nx, long long ny, const double *x,
+                             const double *y, double dx, double dy, double sdd_thresh, double f_min,
+                             double *pts_compact, long long *roots_compact, long long capacity,
+                             long long *count, cudaStream_t s) {
+    const RidgeArgs R = make_ridge_args(f, ev, ev_pixel_stride, ev_comp_stride, nx, ny, x, y, dx, dy,
+                                        sdd_thresh, f_min);
+    const long long np = nx * ny;
+    B2_REQUIRE(np < 2147483647LL, "grid too large for 32-bit component labels (%lld pixels)", np);
+    const unsigned nb = blocks_for(np);
+    Scratch parent(sizeof(int) * np, s), counts(sizeof(int) * nb, s), offsets(sizeof(long long) * nb, s);
+    int *par = static_cast<int *>(parent.ptr);
+    ridge_flag_kernel<<<nb, kTB, 0, s>>>(R, par, static_cast<int *>(counts.ptr));
+    scan_counts_kernel<<<1, 1024, 0, s>>>(static_cast<const int *>(counts.ptr), nb,
+                                          static_cast<long long *>(offsets.ptr), count);
+    ridge_merge_kernel<<<nb, kTB, 0, s>>>(par, nx, ny);
+    if (pts_compact && roots_compact && capacity > 0)
+        ridge_compact_roots_kernel<<<nb, kTB, 0, s>>>(R, par, static_cast<const long long *>(offsets.ptr),
+                                                      pts_compact, roots_compact, capacity);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stride, long long ev_comp_stride,
+                      long long nx, long long ny, const double *x, const double *y, double dx, double dy,
+                      double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
+                      double *pts_compact, long long capacity, long long *count, cudaStream_t s) {
+    const RidgeArgs R = make_ridge_args(f, ev, ev_pixel_stride, ev_comp_stride, nx, ny, x, y, dx, dy,
+                                        sdd_thresh, f_min);
     const long long np = nx * ny;
     const unsigned nb = blocks_for(np);
     const bool want_count = count != nullptr;

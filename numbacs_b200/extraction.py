@@ -8,8 +8,13 @@ pixel order of the reference's ``r_pts[ridge_bool, :]``.  ``np.percentile(f, per
 two order statistics found by a radix select on the device, combined with numba's interpolation
 formula (numba/np/arraymath.py: rank = 1 + (n-1) p/100, lower (1-m) + upper m).
 
-The serial linking of ridge points into curves (ridges.py:418-1054) is host-side geometry and is
-not part of this package.
+ftle_ridges (ridges.py:175-229) groups the ridge points into 8-connected ridges: the reference
+labels ridge_bool with scipy.ndimage.label and gathers each label with a full-grid comparison;
+here a union-find kernel labels the ridge pixels on the device and only the (few) ridge points
+are grouped on the host.
+
+The serial greedy linking of ridge points into ORDERED curves (ftle_ordered_ridges,
+ridges.py:418-1054) is host-side geometry and is not part of this package.
 """
 import ctypes as C
 from math import floor
@@ -18,7 +23,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["ftle_ridge_pts", "percentile_value"]
+__all__ = ["ftle_ridge_pts", "ftle_ridges", "percentile_value"]
 
 
 def percentile_value(f, percentile):
@@ -108,3 +113,36 @@ def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *
     xs, ys = _lib.arg_in(x).obj, _lib.arg_in(y).obj
     h = min(float(xs[1] - xs[0]), float(ys[1] - ys[0]))
     return r_pts, r_vec, sdd, h
+
+
+def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts=3):
+    """Connected FTLE ridges -> list of (k_i, 2) arrays, one per 8-connected group of ridge pixels
+    with at least min_ridge_pts points, in scipy.ndimage.label's (raster) order; points inside a
+    ridge are in raveled pixel order, as in the reference."""
+    fa, xa, ya = _lib.arg_in(f), _lib.arg_in(x), _lib.arg_in(y)
+    if fa.obj.ndim != 2:
+        raise ValueError("f must have shape (nx, ny)")
+    nx, ny = int(fa.obj.shape[0]), int(fa.obj.shape[1])
+    ev, ps, cs = _eigvec_in(eigvec_max, nx, ny)
+    f_min = 0.0 if percentile == 0 else percentile_value(fa.obj, percentile)
+    L = _lib.load()
+    stream = _lib.current_stream(fa.on_device)
+    count = np.zeros(1, np.int64)
+    cap = max(4096, (nx * ny) // 32)
+    for _ in range(2):
+        pts = np.empty((cap, 2), np.float64)
+        roots = np.empty(cap, np.int64)
+        _lib.check(L.b200cs_ftle_ridges(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+                                        float(sdd_thresh), f_min, C.c_void_p(pts.ctypes.data),
+                                        C.c_void_p(roots.ctypes.data), cap,
+                                        C.c_void_p(count.ctypes.data), stream))
+        n = int(count[0])
+        if n <= cap:
+            break
+        cap = n
+    pts, roots = pts[:n], roots[:n]
+    order = np.argsort(roots, kind="stable")          # ascending root = label order; stable keeps
+    sroots = roots[order]                             # the raveled order inside each ridge
+    cuts = np.flatnonzero(np.diff(sroots)) + 1
+    groups = np.split(order, cuts) if n else []
+    return [pts[g] for g in groups if len(g) >= min_ridge_pts]

@@ -398,3 +398,22 @@ def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
 def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
     r_pts, _, sdd, _ = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)
     return r_pts[sdd < -sdd_thresh][:, :2]  # sdd is c2 (< -sdd_thresh <= 0) at ridge points, else 0
+
+
+def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts=3):
+    """ftle_ridges (extraction/ridges.py:175-229): the reference labels ridge_bool with
+    scipy.ndimage.label (8-connectivity) -- third-party code present here, called the same way --
+    and lists each label's points in raveled order."""
+    from scipy.ndimage import generate_binary_structure, label
+    f = _f64(f)
+    nx, ny = f.shape
+    r_pts, _, sdd, _ = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)
+    ridge_bool = (sdd < -sdd_thresh).reshape(nx, ny)
+    labels, nlabels = label(ridge_bool, structure=generate_binary_structure(2, 2))
+    flat = labels.ravel()
+    out = []
+    for i in range(1, nlabels + 1):
+        inds = np.flatnonzero(flat == i)
+        if len(inds) >= min_ridge_pts:
+            out.append(r_pts[inds, :2])
+    return out

@@ -131,6 +131,17 @@ def main():
         rp, rv, sdd, hmin = ridges._ftle_ridge_pts_connect(f, ev, xr, yr, thr, pct)
         G["ridge_conn_pts_" + tag], G["ridge_conn_vec_" + tag], G["ridge_conn_sdd_" + tag] = rp, rv, sdd
     G["ridge_args"] = np.array([[0.0, 0], [10.0, 0], [0.0, 60]])
+    # connected ridges: the reference's pickled golden (tests/test_extraction.py:15-21) and the
+    # real ftle_ridges on the seeded field, stored as one stacked array + the ridge lengths
+    import pickle
+    with open(os.path.join(td, "ridges.pkl"), "rb") as fh:
+        rd = pickle.load(fh)
+    G["ref_ridges_cat"], G["ref_ridges_len"] = np.concatenate(rd), np.array([len(r) for r in rd])
+    for tag, (thr, pct, mrp) in (("a", (0.0, 0, 3)), ("b", (10.0, 60, 1))):
+        rr = ridges.ftle_ridges(f, ev, xr, yr, thr, pct, mrp)
+        G["ridges_cat_" + tag] = np.concatenate(rr)
+        G["ridges_len_" + tag] = np.array([len(r) for r in rr])
+    G["ridges_args"] = np.array([[0.0, 0, 3], [10.0, 60, 1]])
 
     out = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(out, **G)

@@ -216,3 +216,43 @@ def test_ridge_pipeline_on_a_real_ftle_field(nb, oracle):
     j = np.rint(rr[:, 1] / dy).astype(int)
     assert (np.abs(rr[:, 0] - x[i]) <= dx / 2 + 1e-12).all() and (np.abs(rr[:, 1] - y[j]) <= dy / 2 + 1e-12).all()
     assert (ftle_h[i, j] > np.percentile(ftle_h, 50)).all()
+
+
+def _check_ridges(ridges, cat, lens, exact):
+    assert [len(r) for r in ridges] == list(lens)
+    got = np.concatenate(ridges)
+    assert np.array_equal(got, cat) if exact else np.allclose(got, cat)
+
+
+def test_ftle_ridges_golden_and_reference(nb, golden, coords_dg):
+    """tests/test_extraction.py:15-21 (ridges.pkl) and frozen outputs of the real ftle_ridges:
+    GPU union-find labelling == scipy.ndimage.label grouping, label order and point order included."""
+    x, y = coords_dg
+    r = nb.extraction.ftle_ridges(golden["ref_ftle"], golden["ref_Cevecs"][:, :, :, 1], x, y)
+    _check_ridges(r, golden["ref_ridges_cat"], golden["ref_ridges_len"], exact=False)
+    f, ev, xr, yr = golden["ridge_f"], golden["ridge_ev"], golden["ridge_x"], golden["ridge_y"]
+    for tag, (thr, pct, mrp) in zip("ab", golden["ridges_args"]):
+        r = nb.extraction.ftle_ridges(f, ev, xr, yr, thr, int(pct), int(mrp))
+        _check_ridges(r, golden["ridges_cat_" + tag], golden["ridges_len_" + tag], exact=True)
+
+
+def test_ftle_ridges_long_winding_components(nb, oracle):
+    """Components that wind across many thread blocks (spirals, a comb, diagonal staircases):
+    the union-find must agree with scipy's labelling whatever the merge order."""
+    n = 257
+    x, y = np.linspace(0, 1, n), np.linspace(0, 1, n + 30)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    R, TH = np.hypot(X - 0.5, Y - 0.5), np.arctan2(Y - 0.5, X - 0.5)
+    rng = np.random.default_rng(5)
+    fields = [1.0 + np.cos(40 * R - 3 * TH),                       # three-armed spiral ridges
+              1.0 + np.cos(60 * X) * (Y > 0.1) + np.cos(60 * Y) * (Y <= 0.1),   # comb joined by a spine
+              1.0 + np.cos(50 * (X + Y)) + 0.05 * rng.normal(size=X.shape)]     # noisy diagonals
+    for f in fields:
+        gx, gy = np.gradient(f, x, y)
+        nrm = np.hypot(gx, gy) + 1e-300
+        ev = np.stack([gx / nrm, gy / nrm], -1)                    # ridge normal ~ gradient direction
+        r = nb.extraction.ftle_ridges(f, ev, x, y, 0.0, 0, 1)
+        ro = oracle.ftle_ridges(f, ev, x, y, 0.0, 0, 1)
+        assert len(r) == len(ro) and len(r) > 0
+        assert [len(a) for a in r] == [len(a) for a in ro]
+        assert np.array_equal(np.concatenate(r), np.concatenate(ro))

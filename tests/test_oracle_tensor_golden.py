@@ -128,3 +128,23 @@ def test_ftle_ridge_pts_match_real_reference_bitwise(oracle, golden):
         assert np.array_equal(rp, golden["ridge_conn_pts_" + tag])
         assert np.array_equal(rv, golden["ridge_conn_vec_" + tag])
         assert np.array_equal(sdd, golden["ridge_conn_sdd_" + tag])
+
+
+def _check_ridges(ridges, cat, lens, exact):
+    assert [len(r) for r in ridges] == list(lens)
+    got = np.concatenate(ridges)
+    assert np.array_equal(got, cat) if exact else np.allclose(got, cat)
+
+
+def test_ftle_ridges_golden(oracle, golden, coords_dg):
+    """tests/test_extraction.py:15-21 of the reference (ridges.pkl)."""
+    x, y = coords_dg
+    r = oracle.ftle_ridges(golden["ref_ftle"], golden["ref_Cevecs"][:, :, :, 1], x, y)
+    _check_ridges(r, golden["ref_ridges_cat"], golden["ref_ridges_len"], exact=False)
+
+
+def test_ftle_ridges_match_real_reference(oracle, golden):
+    f, ev, x, y = golden["ridge_f"], golden["ridge_ev"], golden["ridge_x"], golden["ridge_y"]
+    for tag, (thr, pct, mrp) in zip("ab", golden["ridges_args"]):
+        r = oracle.ftle_ridges(f, ev, x, y, thr, int(pct), int(mrp))
+        _check_ridges(r, golden["ridges_cat_" + tag], golden["ridges_len_" + tag], exact=True)
