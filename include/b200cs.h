@@ -262,6 +262,14 @@ B200CS_API int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, 
                        int64_t *roots_compact /*[capacity]*/, int64_t capacity, int64_t *count,
                        void *stream);
 
+/* flowmap_composition(flowmaps, grid, nT)      (integration.py:609-644)
+ * flowmaps is [nT, nx, ny, 2] (the flow maps over [t0 + k h, t0 + (k+1) h]), grid6 =
+ * {x0, x1, nx, y0, y1, ny} (the UCGrid tuple, host or device); composed [nx, ny, 2] =
+ * flowmaps[nT-1] o ... o flowmaps[1] o flowmaps[0] by bilinear interpolation with CONSTANT
+ * extrapolation (0 outside the grid), all nT-1 interpolation passes fused into one kernel. */
+B200CS_API int b200cs_flowmap_composition(const double *flowmaps, const double *grid6, int64_t nT,
+                               double *composed, void *stream);
+
 /* out2 = { sorted(data)[k], sorted(data)[min(k+1, n-1)] } by radix select (no sort, data is not
  * modified): the two order statistics np.percentile interpolates between (ridges.py:45, 279). */
 B200CS_API int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream);

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "b200cs_ftle_ridge_pts": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp,
                               _i64, _vp, _vp],
     "b200cs_ftle_ridges": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _i64, _vp, _vp],
+    "b200cs_flowmap_composition": [_vp, _vp, _i64, _vp, _vp],
     "b200cs_order_stats": [_vp, _i64, _i64, _vp, _vp],
     "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
 }

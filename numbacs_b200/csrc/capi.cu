@@ -900,6 +900,27 @@ int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_
     });
 }
 
+int b200cs_flowmap_composition(const double *flowmaps, const double *grid6, int64_t nT, double *composed,
+                               void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmaps && grid6 && composed, "null argument");
+        B2_REQUIRE(nT >= 1, "nT must be at least 1 (got %lld)", (long long)nT);
+        double g[6];
+        B2_CHECK_CUDA(cudaMemcpy(g, grid6, sizeof(g), cudaMemcpyDefault));
+        const long long nx = (long long)g[2], ny = (long long)g[5];
+        B2_REQUIRE(nx >= 2 && ny >= 2, "the grid needs at least 2 points per axis");
+        B2_REQUIRE(g[1] > g[0] && g[4] > g[3], "grid axes must be ascending");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmaps, np * 2 * nT, s);
+        Out<double> dout(composed, np * 2, s);
+        launch_composition(dfm.dev, g, nT, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream) {
     return guarded([&] {
         require_device();

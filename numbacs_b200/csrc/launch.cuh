@@ -82,6 +82,8 @@ void launch_ridge_components(const double *f, const double *ev, long long ev_pix
                              const double *y, double dx, double dy, double sdd_thresh, double f_min,
                              double *pts_compact, long long *roots_compact, long long capacity,
                              long long *count, cudaStream_t s);
+void launch_composition(const double *flowmaps, const double *grid6 /*host*/, long long nT, double *out,
+                        cudaStream_t s);
 void launch_order_stats(const double *data, long long n, long long k, double *out2, cudaStream_t s);
 
 }  // namespace b200cs

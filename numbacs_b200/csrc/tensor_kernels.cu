@@ -428,6 +428,53 @@ ridge_compact_roots_kernel(const __grid_constant__ RidgeArgs R, const int *__res
     }
 }
 
+// ---- flow-map composition (flowmap_composition, integration.py:609-644) --------------------------
+// composed = F_{nT-1}( ... F_2(F_1(F_0)) ... ): every grid point walks through the chain of
+// intermediate flow maps by bilinear interpolation (interpolation.splines.eval_linear on the 2-D
+// grid, CONSTANT extrapolation: a component evaluated outside the grid is 0).  The reference makes
+// 2 (nT-1) full-grid eval_linear passes through a points array; here ONE kernel keeps the running
+// position in registers and gathers the four (x, y) taps of each map as double2 -- 16 B read +
+// 16 B written per point of HBM traffic, the (nT-1) x 64 B of gathers are L2 hits (a flow map is
+// smooth: neighbouring threads hit neighbouring cells).
+struct Grid2 {
+    double a[2], b[2], delta[2], inv_delta[2];
+    int n[2];
+};
+
+__device__ __forceinline__ void locate2(const Grid2 &g, int d, double x, int &i, double &lam) {
+    const double dd = x - g.a[d];
+    double fi = floor(dd * g.inv_delta[d]);
+    fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
+    i = (int)fi;
+    lam = __dsub_rn(dd, __dmul_rn(fi, g.delta[d])) * g.inv_delta[d];
+}
+
+__device__ __forceinline__ double2 bilinear2(const Grid2 &g, const double2 *__restrict__ F, double px, double py) {
+    if (px < g.a[0] || px > g.b[0] || py < g.a[1] || py > g.b[1]) return make_double2(0.0, 0.0);
+    int i0, i1;
+    double l0, l1;
+    locate2(g, 0, px, i0, l0);
+    locate2(g, 1, py, i1, l1);
+    const double2 *c = F + (long long)i0 * g.n[1] + i1;
+    const double2 c00 = __ldg(c), c01 = __ldg(c + 1), c10 = __ldg(c + g.n[1]), c11 = __ldg(c + g.n[1] + 1);
+    const double m1 = 1.0 - l1, m0 = 1.0 - l0;
+    double2 v;
+    v.x = fma(l0, fma(l1, c11.x, m1 * c10.x), m0 * fma(l1, c01.x, m1 * c00.x));
+    v.y = fma(l0, fma(l1, c11.y, m1 * c10.y), m0 * fma(l1, c01.y, m1 * c00.y));
+    return v;
+}
+
+__global__ void __launch_bounds__(kTB)
+composition_kernel(const double2 *__restrict__ fms, const __grid_constant__ Grid2 g, long long nT,
+                   double2 *__restrict__ out) {
+    const long long np = (long long)g.n[0] * g.n[1];
+    const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
+    if (q >= np) return;
+    double2 p = __ldg(fms + q);
+    for (long long k = 1; k < nT - 1; ++k) p = bilinear2(g, fms + k * np, p.x, p.y);
+    out[q] = bilinear2(g, fms + (nT - 1) * np, p.x, p.y);
+}
+
 // ---- order statistics: sorted(data)[k] and sorted(data)[k+1] by MSB-first radix select ----------
 struct SelectState {
     unsigned long long prefix, mask;  // key bits fixed so far
@@ -622,6 +669,22 @@ void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stri
             B2_CHECK_CUDA(cudaGetLastError());
         }
     }
+}
+
+void launch_composition(const double *flowmaps, const double *grid6, long long nT, double *out, cudaStream_t s) {
+    B2_REQUIRE((reinterpret_cast<uintptr_t>(flowmaps) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "flow maps must be 16-byte aligned");
+    Grid2 g{};
+    for (int d = 0; d < 2; ++d) {
+        g.a[d] = grid6[3 * d];
+        g.b[d] = grid6[3 * d + 1];
+        g.n[d] = (int)grid6[3 * d + 2];
+        g.delta[d] = (g.b[d] - g.a[d]) / (double)(g.n[d] - 1);
+        g.inv_delta[d] = 1.0 / g.delta[d];
+    }
+    composition_kernel<<<blocks_for((long long)g.n[0] * g.n[1]), kTB, 0, s>>>(
+        reinterpret_cast<const double2 *>(flowmaps), g, nT, reinterpret_cast<double2 *>(out));
+    B2_CHECK_CUDA(cudaGetLastError());
 }
 
 void launch_order_stats(const double *data, long long n, long long k, double *out2, cudaStream_t s) {

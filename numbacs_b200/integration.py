@@ -20,7 +20,8 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D"]
+__all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D",
+           "flowmap_composition", "flowmap_composition_initial", "flowmap_composition_step"]
 
 
 def _method(method):
@@ -130,3 +131,76 @@ def flowmap_aux_grid_2D(funcptr, t0, T, x, y, params, h=1e-5, eig_main=True, com
         float(atol), ma.ptr, out.ptr, status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
     _fill_info(info, status, steps, stats)
     return out.obj
+
+
+# ---- flow-map composition (integration.py:609-737): FTLE time series from short flow maps ----------
+
+def _grid6(grid):
+    return np.ascontiguousarray([[float(g[0]), float(g[1]), float(g[2])] for g in grid],
+                                dtype=np.float64).ravel()
+
+
+def flowmap_composition(flowmaps, grid, nT, *, device_out=False):
+    """Composed flow map (nx, ny, 2) from the nT intermediate flow maps (nT, nx, ny, 2): bilinear
+    interpolation on `grid` = ((x0, x1, nx), (y0, y1, ny)), 0 outside the grid (the reference's
+    eval_linear(..., xto.CONSTANT)), all passes fused into one kernel."""
+    fa = _lib.arg_in(flowmaps)
+    g = _grid6(grid)
+    nx, ny = int(grid[0][2]), int(grid[1][2])
+    if tuple(int(v) for v in fa.obj.shape) != (int(nT), nx, ny, 2):
+        raise ValueError(f"flowmaps must have shape {(int(nT), nx, ny, 2)}")
+    dev = bool(device_out or fa.on_device)
+    out = _lib.alloc_out((nx, ny, 2), np.float64, dev)
+    _lib.check(_lib.load().b200cs_flowmap_composition(fa.ptr, C.c_void_p(g.ctypes.data), int(nT),
+                                                      out.ptr, _lib.current_stream(dev)))
+    return out.obj
+
+
+def _flowmap_into(dst, funcptr, t0, h, x, y, params, kwargs):
+    """flowmap_grid_2D written straight into dst (a (nx, ny, 2) slice of the flowmaps array)."""
+    kw = dict(kwargs)
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(kw.pop("mask", None))
+    method, rtol, atol = kw.pop("method", "dop853"), kw.pop("rtol", 1e-6), kw.pop("atol", 1e-8)
+    if kw:
+        raise TypeError(f"unexpected keyword arguments {sorted(kw)}")
+    on_dev = _lib._is_torch(dst)
+    ptr = C.c_void_p(dst.data_ptr() if on_dev else dst.ctypes.data)
+    _lib.check(_lib.load().b200cs_flowmap_grid_2d(
+        int(funcptr), float(t0), float(h), xa.ptr, int(xa.obj.shape[0]), ya.ptr, int(ya.obj.shape[0]),
+        pa.ptr, int(pa.obj.shape[0]), _method(method), float(rtol), float(atol), ma.ptr, 0, ptr, None,
+        None, None, None, _lib.current_stream(on_dev)))
+
+
+def _new_flowmaps(nT, nx, ny, device):
+    if device:
+        import torch
+        return torch.zeros((nT, nx, ny, 2), dtype=torch.float64, device="cuda")
+    return np.zeros((nT, nx, ny, 2), np.float64)
+
+
+def flowmap_composition_initial(funcptr, t0, T, h, x, y, grid, params, *, device_out=False, **kwargs):
+    """First step of the composition method -> (flowmap0 (nx, ny, 2), flowmaps (nT, nx, ny, 2), nT)
+    with nT = |round(T / h)|; flowmaps[k] is the flow map over [t0 + k h, t0 + (k + 1) h]."""
+    nT = abs(round(T / h))
+    nx, ny = int(grid[0][2]), int(grid[1][2])
+    dev = bool(device_out or _lib._is_torch(x) and x.is_cuda)
+    flowmaps = _new_flowmaps(nT, nx, ny, dev)
+    for k in range(nT):
+        _flowmap_into(flowmaps[k], funcptr, t0, h, x, y, params, kwargs)
+        t0 += h
+    return flowmap_composition(flowmaps, grid, nT, device_out=dev), flowmaps, nT
+
+
+def flowmap_composition_step(flowmaps, funcptr, t0, h, nT, x, y, grid, params, **kwargs):
+    """Next step: drops flowmaps[0], appends the flow map over [t0, t0 + h] (integrated on the GPU,
+    in place) and composes -> (flowmap_k, flowmaps).  Like the reference, `flowmaps` is updated in
+    place when it is a float64 numpy array or CUDA tensor."""
+    if _lib._is_torch(flowmaps):
+        flowmaps[:-1] = flowmaps[1:].clone()
+    else:
+        flowmaps = np.asarray(flowmaps)
+        if flowmaps.dtype != np.float64 or not flowmaps.flags.c_contiguous:
+            flowmaps = np.ascontiguousarray(flowmaps, dtype=np.float64)
+        flowmaps[:-1] = flowmaps[1:].copy()
+    _flowmap_into(flowmaps[-1], funcptr, t0, h, x, y, params, kwargs)
+    return flowmap_composition(flowmaps, grid, nT), flowmaps

@@ -96,6 +96,7 @@ def lib():
         L.oracle_ftle_ridge_pts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                             C.c_void_p, C.c_double, C.c_double, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
+        L.oracle_flowmap_composition.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -417,3 +418,32 @@ def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts
         if len(inds) >= min_ridge_pts:
             out.append(r_pts[inds, :2])
     return out
+
+
+def _grid6(grid):
+    return _f64(np.array([[g[0], g[1], float(g[2])] for g in grid]).ravel())
+
+
+def flowmap_composition(flowmaps, grid, nT):
+    fms = _f64(flowmaps)
+    g = _grid6(grid)
+    nx, ny = int(grid[0][2]), int(grid[1][2])
+    out = np.zeros((nx, ny, 2))
+    lib().oracle_flowmap_composition(_ptr(fms), _ptr(g), int(nT), _ptr(out))
+    return out
+
+
+def flowmap_composition_initial(flow, t0, T, h, x, y, grid, params, **kwargs):
+    nT = abs(round(T / h))
+    flowmaps = np.zeros((nT, int(grid[0][2]), int(grid[1][2]), 2))
+    for k in range(nT):
+        flowmaps[k] = flowmap_grid_2D(flow, t0, h, x, y, params, **kwargs)
+        t0 += h
+    return flowmap_composition(flowmaps, grid, nT), flowmaps, nT
+
+
+def flowmap_composition_step(flowmaps, flow, t0, h, nT, x, y, grid, params, **kwargs):
+    flowmaps = _f64(flowmaps).copy()
+    flowmaps[:-1] = flowmaps[1:].copy()
+    flowmaps[-1] = flowmap_grid_2D(flow, t0, h, x, y, params, **kwargs)
+    return flowmap_composition(flowmaps, grid, nT), flowmaps

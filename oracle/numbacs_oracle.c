@@ -17,6 +17,8 @@
  *     (np.linalg.eigh on 2x2 = LAPACK dlaev2, restated; pinned by Cevals/Cevecs*.npy and by the
  *     live numbacs.diagnostics.C_eig_2D, which imports here)
  *   - FTLE ridge points                      src/numbacs/extraction/ridges.py:9-76, 232-318
+ *   - flow-map composition                   src/numbacs/integration.py:609-737 (bilinear
+ *     interpolation.splines.eval_linear, CONSTANT extrapolation; pinned by fm_ci/fm_cs.npy)
  *
  * The arithmetic of the ODE solver and of the spline is NOT in the reference tree: it lives in
  * the third-party packages `numbalsoda` (unpinned, pyproject.toml:32) and `interpolation>=2.2.6`
@@ -882,6 +884,52 @@ int64_t oracle_ftle_ridge_pts(const double *f, const double *evec, int64_t nx, i
             }
         }
     return count;
+}
+
+/* ------------------------------------------------------------------ flow-map composition */
+
+/* eval_linear(grid, F, pts, xto.CONSTANT) on a 2-D grid ((a0,b0,n0),(a1,b1,n1)); F has element
+ * stride `st` (flowmaps[k, :, :, c] is a strided view).  Outside the grid -> 0. */
+static double eval_linear2(const double *g6, const double *F, int64_t st, double p0, double p1)
+{
+    double a0 = g6[0], b0 = g6[1], a1 = g6[3], b1 = g6[4];
+    int64_t n0 = (int64_t)g6[2], n1 = (int64_t)g6[5];
+    if (p0 < a0 || p0 > b0 || p1 < a1 || p1 > b1) return 0.0;
+    int64_t i0, i1;
+    double l0, l1;
+    axis_locate(a0, b0, n0, p0, &i0, &l0);
+    axis_locate(a1, b1, n1, p1, &i1, &l1);
+    const double *c = F + (i0 * n1 + i1) * st;
+    double v = 0.0;
+    for (int a = 0; a < 2; ++a) {
+        double wa = a ? l0 : 1.0 - l0;
+        const double *cc = c + a * n1 * st;
+        v += wa * ((1.0 - l1) * cc[0] + l1 * cc[st]);
+    }
+    return v;
+}
+
+/* flowmap_composition (integration.py:609-644): flowmaps[nT, nx, ny, 2] -> composed[nx, ny, 2].
+ * pts = flowmaps[0]; for k in 1..nT-2: pts = flowmaps[k](pts); composed = flowmaps[nT-1](pts)
+ * (so nT == 1 applies flowmaps[0] to itself, as the reference does). */
+void oracle_flowmap_composition(const double *flowmaps, const double *grid6, int64_t nT,
+                                double *composed)
+{
+    int64_t nx = (int64_t)grid6[2], ny = (int64_t)grid6[5], np = nx * ny;
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < np; ++q) {
+        double px = flowmaps[2 * q], py = flowmaps[2 * q + 1];
+        for (int64_t k = 1; k < nT - 1; ++k) {
+            const double *F = flowmaps + k * np * 2;
+            double fx = eval_linear2(grid6, F, 2, px, py);
+            double fy = eval_linear2(grid6, F + 1, 2, px, py);
+            px = fx;
+            py = fy;
+        }
+        const double *F = flowmaps + (nT - 1) * np * 2;
+        composed[2 * q] = eval_linear2(grid6, F, 2, px, py);
+        composed[2 * q + 1] = eval_linear2(grid6, F + 1, 2, px, py);
+    }
 }
 
 /* ------------------------------------------------------------------ helpers ------------ */

@@ -49,7 +49,7 @@ def main():
     G = {}
     td = os.path.join(REF, "tests", "testing_data")
     for name in ("fm", "fm_n", "ftle", "lavd", "vort", "fm_aux", "C", "Cevals", "Cevecs",
-                 "Cevals_aux", "Cevecs_aux", "ridge_pts"):
+                 "Cevals_aux", "Cevecs_aux", "ridge_pts", "fm_ci", "fms_ci", "fm_cs", "fms_cs"):
         G["ref_" + name] = np.load(os.path.join(td, name + ".npy"))
 
     tf = os.path.join(REF, "tests", "test_flows.py")

@@ -256,3 +256,58 @@ def test_ftle_ridges_long_winding_components(nb, oracle):
         assert len(r) == len(ro) and len(r) > 0
         assert [len(a) for a in r] == [len(a) for a in ro]
         assert np.array_equal(np.concatenate(r), np.concatenate(ro))
+
+
+# ------------------------------------------------------------------ flow-map composition
+
+def test_flowmap_composition_golden(nb, golden, coords_dg):
+    """tests/test_integration.py:92-114 of the reference (fm_ci / fms_ci / fm_cs / fms_cs.npy)."""
+    from test_oracle_tensor_golden import check_composition_initial
+    I = nb.integration
+    x, y = coords_dg
+    grid = ((x[0], x[-1], 21), (y[0], y[-1], 11))
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    fm0, fms, nT = I.flowmap_composition_initial(f, 0.0, 8.0, 1.0, x, y, grid, p)
+    assert fm0.shape == (21, 11, 2) and fms.shape == (8, 21, 11, 2)
+    check_composition_initial(fm0, fms, nT, golden)
+    fms_in = golden["ref_fms_ci"].astype(np.float64)
+    fmk, fms2 = I.flowmap_composition_step(fms_in, f, 8.0, 1.0, 8, x, y, grid, p)
+    assert np.allclose(fmk.astype(np.float32), golden["ref_fm_cs"])
+    assert np.allclose(fms2.astype(np.float32), golden["ref_fms_cs"])
+    assert fms2 is fms_in                                   # updated in place, like the reference
+
+
+def test_flowmap_composition_vs_oracle_device_resident(nb, oracle):
+    import torch
+    I = nb.integration
+    nx, ny, nT = 301, 151, 10
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    grid = ((x[0], x[-1], nx), (y[0], y[-1], ny))
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    fm0, fms, n = I.flowmap_composition_initial(f, 0.0, -10.0, -1.0, xd, yd, grid, p)
+    assert n == nT and fm0.is_cuda and fms.is_cuda and fms.shape == (nT, nx, ny, 2)
+    # each intermediate map is the plain flow map over its own interval
+    k = 3
+    assert np.array_equal(fms[k].cpu().numpy(), I.flowmap_grid_2D(f, -3.0, -1.0, x, y, p))
+    # oracle composition of the SAME intermediate maps; the walls are left out (positions there
+    # sit within an ulp of the grid edge, where CONSTANT extrapolation switches to 0)
+    ref = oracle.flowmap_composition(fms.cpu().numpy(), grid, nT)
+    got = fm0.cpu().numpy()
+    assert np.abs(got - ref)[1:-1, 1:-1].max() <= 1e-13
+    # on the GPU the wall particles never leave the wall (exact zero normal velocity)
+    assert np.array_equal(got[-1, :, 0], np.full(ny, 2.0)) and np.array_equal(got[:, -1, 1], np.full(nx, 1.0))
+    # step: same as recomputing from scratch one interval later
+    fmk, fms = I.flowmap_composition_step(fms, f, -10.0, -1.0, nT, xd, yd, grid, p)
+    fm0b, fmsb, _ = I.flowmap_composition_initial(f, -1.0, -10.0, -1.0, xd, yd, grid, p)
+    assert torch.equal(fms, fmsb) and torch.equal(fmk, fm0b)
+    # the composed map approximates the directly integrated one
+    direct = I.flowmap_grid_2D(f, 0.0, -10.0, x, y, p)
+    assert np.median(np.abs(got - direct)) < 2e-3
+    # a point that leaves the grid gets 0 (CONSTANT extrapolation); nT = 1 applies the map to itself
+    fms1 = fms[:1].clone()
+    one = I.flowmap_composition(fms1, grid, 1)
+    assert np.abs(one.cpu().numpy() - oracle.flowmap_composition(fms1.cpu().numpy(), grid, 1))[1:-1, 1:-1].max() <= 1e-13
+    fms[0, 5, 7, 0] = 2.5
+    out = I.flowmap_composition(fms, grid, nT)
+    assert not out[5, 7].any()

@@ -148,3 +148,40 @@ def test_ftle_ridges_match_real_reference(oracle, golden):
     for tag, (thr, pct, mrp) in zip("ab", golden["ridges_args"]):
         r = oracle.ftle_ridges(f, ev, x, y, thr, int(pct), int(mrp))
         _check_ridges(r, golden["ridges_cat_" + tag], golden["ridges_len_" + tag], exact=True)
+
+
+def check_composition_initial(fm0, fms, nT, golden):
+    """fm_ci.npy / fms_ci.npy.  The wall row x = 2 is left out of the fm_ci comparison: there the
+    reference's particles sit at 2 +- a few 1e-16 (rounding noise of its wall velocity, which
+    depends on the libm of the machine the golden was made on); when the interpolated position
+    lands above 2 by one ulp the CONSTANT extrapolation returns 0, which is what fm_ci.npy holds
+    for that row -- noise, not signal.  Either outcome is accepted there."""
+    assert nT == 8
+    assert np.array_equal(fms.astype(np.float32), golden["ref_fms_ci"])
+    assert np.allclose(fm0[:20].astype(np.float32), golden["ref_fm_ci"][:20])
+    wall = fm0[20]
+    assert np.all((wall == 0.0).all(axis=1) | (np.abs(wall[:, 0] - 2.0) < 1e-12))
+
+
+def test_flowmap_composition_golden(oracle, golden, coords_dg):
+    """tests/test_integration.py:92-114 of the reference (fm_ci / fms_ci / fm_cs / fms_cs.npy)."""
+    x, y = coords_dg
+    grid = ((x[0], x[-1], 21), (y[0], y[-1], 11))
+    f, p, _ = oracle.get_predefined_flow("double_gyre")
+    fm0, fms, nT = oracle.flowmap_composition_initial(f, 0.0, 8.0, 1.0, x, y, grid, p)
+    check_composition_initial(fm0, fms, nT, golden)
+    fmk, fms2 = oracle.flowmap_composition_step(golden["ref_fms_ci"].astype(np.float64), f, 8.0, 1.0,
+                                                8, x, y, grid, p)
+    assert np.allclose(fmk.astype(np.float32), golden["ref_fm_cs"])
+    assert np.allclose(fms2.astype(np.float32), golden["ref_fms_cs"])
+    # the composed map approximates the directly integrated one (it is an interpolation scheme)
+    direct = oracle.flowmap_grid_2D(f, 0.0, 8.0, x, y, p)
+    assert np.abs(fm0 - direct).max() < 0.5 and np.median(np.abs(fm0 - direct)) < 0.05
+    # points that leave the grid get 0 (CONSTANT extrapolation), per component
+    fms3 = fms.copy()
+    fms3[0, 3, 4] = (2.5, 0.5)
+    fms3[0, 5, 6] = (1.0, -1e-9)
+    out = oracle.flowmap_composition(fms3, grid, 8)
+    assert not out[3, 4].any() and not out[5, 6].any()
+    assert np.array_equal(np.delete(out.reshape(-1, 2), [3 * 11 + 4, 5 * 11 + 6], axis=0),
+                          np.delete(fm0.reshape(-1, 2), [3 * 11 + 4, 5 * 11 + 6], axis=0))
