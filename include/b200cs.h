@@ -52,6 +52,7 @@ extern "C" {
 #define B200CS_FLOW_BICKLEY_JET 1 /* flows.py:1182-1213, 12 params */
 #define B200CS_FLOW_ABC 2         /* flows.py:1249-1258, 5 params, 3-D state */
 #define B200CS_FLOW_SPLINE2D 3    /* flows.py:156-253, 1 param (int_direction) */
+#define B200CS_FLOW_LINEAR2D 4    /* flows.py:458-503 (get_flow_linear_2D), 1 param */
 
 /* extrap_mode of interpolation.splines.eval_spline / eval_linear (flows.py:121, 387, 601) */
 #define B200CS_EXTRAP_CONSTANT 0
@@ -83,6 +84,12 @@ B200CS_API int b200cs_flow_create_analytic(int kind, int *out_handle);
  * grid9 = {t0,t1,nt, x0,x1,nx, y0,y1,ny}; Cu/Cv are the (nt+2, nx+2, ny+2) prefilter outputs.
  * The coefficients are copied (interleaved u,v) to the current device. */
 B200CS_API int b200cs_flow_create_spline(const double *grid9, const double *Cu, const double *Cv,
+                              int spherical, int extrap_mode, double r, int *out_handle);
+
+/* get_flow_linear_2D(grid_vel, U, V, spherical, extrap_mode, r)   (flows.py:418-506)
+ * Same as b200cs_flow_create_spline but over the RAW velocity arrays U, V [nt, nx, ny] with
+ * trilinear interpolation (interpolation.splines.eval_linear) instead of the cubic spline. */
+B200CS_API int b200cs_flow_create_linear(const double *grid9, const double *U, const double *V,
                               int spherical, int extrap_mode, double r, int *out_handle);
 
 /* get_callable_scalar(grid_f, C_eval_f, extrap_mode)          (flows.py:387-415) linear = 0

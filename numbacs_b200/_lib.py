@@ -28,6 +28,7 @@ PROTOTYPES = {
     "b200cs_device_count": [_ip],
     "b200cs_flow_create_analytic": [_i, _ip],
     "b200cs_flow_create_spline": [_vp, _vp, _vp, _i, _i, _d, _ip],
+    "b200cs_flow_create_linear": [_vp, _vp, _vp, _i, _i, _d, _ip],
     "b200cs_scalar_create": [_vp, _vp, _i, _i, _ip],
     "b200cs_flow_destroy": [_i],
     "b200cs_flow_info": [_i, _ip, _ip, _ip],

@@ -111,7 +111,7 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
     R.coef_uv = nullptr;
     R.r = f.r;
     std::memset(&R.grid, 0, sizeof(R.grid));
-    if (f.kind == B200CS_FLOW_SPLINE2D) {
+    if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
         R.grid = make_grid_dev(f);
         R.coef_uv = static_cast<const double2 *>(f.coef);
     }
@@ -257,33 +257,43 @@ int b200cs_flow_create_analytic(int kind, int *out_handle) {
     });
 }
 
+static void create_gridded_flow(const double *grid9, const double *Cu, const double *Cv, int spherical,
+                                int extrap_mode, double r, bool linear, int *out_handle) {
+    require_device();
+    B2_REQUIRE(grid9 && Cu && Cv && out_handle, "null argument");
+    B2_REQUIRE(spherical >= 0 && spherical <= 2, "spherical must be 0, 1 or 2 (got %d)", spherical);
+    B2_REQUIRE(extrap_mode >= 0 && extrap_mode <= 2, "unknown extrap_mode %d", extrap_mode);
+    auto f = std::make_shared<FlowSpec>();
+    f->kind = linear ? B200CS_FLOW_LINEAR2D : B200CS_FLOW_SPLINE2D;
+    f->ndim = 2;
+    f->min_params = 1;
+    f->spherical = spherical;
+    f->extrap = extrap_mode;
+    f->linear = linear ? 1 : 0;
+    f->r = r;
+    read_grid9(grid9, f->grid);
+    B2_CHECK_CUDA(cudaGetDevice(&f->device));
+    const int pad = linear ? 0 : 2;
+    const size_t count = (size_t)(f->grid.n[0] + pad) * (f->grid.n[1] + pad) * (f->grid.n[2] + pad);
+    f->coef_bytes = count * sizeof(double2);
+    B2_CHECK_CUDA(cudaMalloc(&f->coef, f->coef_bytes));
+    cudaStream_t s = nullptr;
+    {
+        In<double> du(Cu, count, s), dv(Cv, count, s);
+        launch_interleave(du.dev, dv.dev, (long long)count, static_cast<double2 *>(f->coef), s);
+        B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    }
+    *out_handle = registry_add(std::move(f));
+}
+
 int b200cs_flow_create_spline(const double *grid9, const double *Cu, const double *Cv, int spherical,
                               int extrap_mode, double r, int *out_handle) {
-    return guarded([&] {
-        require_device();
-        B2_REQUIRE(grid9 && Cu && Cv && out_handle, "null argument");
-        B2_REQUIRE(spherical >= 0 && spherical <= 2, "spherical must be 0, 1 or 2 (got %d)", spherical);
-        B2_REQUIRE(extrap_mode >= 0 && extrap_mode <= 2, "unknown extrap_mode %d", extrap_mode);
-        auto f = std::make_shared<FlowSpec>();
-        f->kind = B200CS_FLOW_SPLINE2D;
-        f->ndim = 2;
-        f->min_params = 1;
-        f->spherical = spherical;
-        f->extrap = extrap_mode;
-        f->r = r;
-        read_grid9(grid9, f->grid);
-        B2_CHECK_CUDA(cudaGetDevice(&f->device));
-        const size_t count = (size_t)(f->grid.n[0] + 2) * (f->grid.n[1] + 2) * (f->grid.n[2] + 2);
-        f->coef_bytes = count * sizeof(double2);
-        B2_CHECK_CUDA(cudaMalloc(&f->coef, f->coef_bytes));
-        cudaStream_t s = nullptr;
-        {
-            In<double> du(Cu, count, s), dv(Cv, count, s);
-            launch_interleave(du.dev, dv.dev, (long long)count, static_cast<double2 *>(f->coef), s);
-            B2_CHECK_CUDA(cudaStreamSynchronize(s));
-        }
-        *out_handle = registry_add(std::move(f));
-    });
+    return guarded([&] { create_gridded_flow(grid9, Cu, Cv, spherical, extrap_mode, r, false, out_handle); });
+}
+
+int b200cs_flow_create_linear(const double *grid9, const double *U, const double *V, int spherical,
+                              int extrap_mode, double r, int *out_handle) {
+    return guarded([&] { create_gridded_flow(grid9, U, V, spherical, extrap_mode, r, true, out_handle); });
 }
 
 int b200cs_scalar_create(const double *grid9, const double *data, int linear, int extrap_mode,

@@ -9,6 +9,8 @@ void launch_flowmap_dg(const IntegArgs &A, int mode, cudaStream_t s);
 void launch_flowmap_bickley(const IntegArgs &A, int mode, cudaStream_t s);
 void launch_flowmap_abc(const IntegArgs &A, int mode, cudaStream_t s);
 void launch_flowmap_spline(int spherical, const IntegArgs &A, int mode, cudaStream_t s);
+void launch_flowmap_linear(int spherical, const IntegArgs &A, int mode, cudaStream_t s);
+void launch_lavd_linear(int spherical, const IntegArgs &A, cudaStream_t s);
 void launch_lavd_dg(const IntegArgs &A, cudaStream_t s);
 void launch_lavd_bickley(const IntegArgs &A, cudaStream_t s);
 void launch_lavd_spline(int spherical, const IntegArgs &A, cudaStream_t s);
@@ -18,6 +20,7 @@ void launch_lavd_flowmap(const FlowSpec &f, const IntegArgs &A, cudaStream_t s) 
     case B200CS_FLOW_DOUBLE_GYRE: launch_lavd_dg(A, s); break;
     case B200CS_FLOW_BICKLEY_JET: launch_lavd_bickley(A, s); break;
     case B200CS_FLOW_SPLINE2D: launch_lavd_spline(f.spherical, A, s); break;
+    case B200CS_FLOW_LINEAR2D: launch_lavd_linear(f.spherical, A, s); break;
     default:
         set_error("LAVD needs a 2-D flow (kind %d)", f.kind);
         throw Fail{B200CS_E_INVALID};
@@ -33,6 +36,9 @@ void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode, cudaStream_
         break;
     case B200CS_FLOW_SPLINE2D:
         launch_flowmap_spline(f.spherical, A, mode, s);
+        break;
+    case B200CS_FLOW_LINEAR2D:
+        launch_flowmap_linear(f.spherical, A, mode, s);
         break;
     default:
         set_error("handle is not a flow (kind %d)", f.kind);
@@ -72,6 +78,11 @@ void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, con
         if (f.spherical == 1) rhs_kernel<Spline2D<1>><<<g, b, 0, s>>>(P, t, y, npts, dy);
         else if (f.spherical == 2) rhs_kernel<Spline2D<2>><<<g, b, 0, s>>>(P, t, y, npts, dy);
         else rhs_kernel<Spline2D<0>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        break;
+    case B200CS_FLOW_LINEAR2D:
+        if (f.spherical == 1) rhs_kernel<Spline2D<1, true>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        else if (f.spherical == 2) rhs_kernel<Spline2D<2, true>><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        else rhs_kernel<Spline2D<0, true>><<<g, b, 0, s>>>(P, t, y, npts, dy);
         break;
     default:
         set_error("handle is not a flow (kind %d)", f.kind);

@@ -36,7 +36,7 @@ struct KernelShape<DoubleGyre, false> {
     static constexpr bool kLockstep = true;
 };
 template <int SPH>
-struct KernelShape<Spline2D<SPH>, false> {
+struct KernelShape<Spline2D<SPH, false>, false> {
     static constexpr int kThreads = 448;   // <= 146 registers
     static constexpr int kMinBlocks = 1;
     static constexpr bool kLockstep = true;

@@ -4,6 +4,7 @@
 // (signature rhs(t, y, dy, p), /root/reference/src/numbacs/flows.py):
 //   DoubleGyre  flows.py:1146-1158      BickleyJet  flows.py:1182-1213
 //   Abc         flows.py:1249-1258      Spline2D    flows.py:156-253 (spherical 0 / 1 / 2)
+//   Spline2D<S, true>  flows.py:458-503 (get_flow_linear_2D)
 // Conventions kept from the reference: tt = p[0]*t, dy = p[0]*v(tt, y) (userguide.rst:217-227);
 // `params` is used verbatim; operation order follows the reference expressions (FMA contraction
 // is allowed, it perturbs results at the 1-ulp level only).
@@ -145,7 +146,10 @@ __device__ __forceinline__ double pymod_pos(double a, double m) {
     return r;
 }
 
-template <int SPHERICAL>
+// LINEAR = true: get_flow_linear_2D (flows.py:418-506), trilinear eval_linear on the raw (u, v)
+// data instead of the tri-cubic spline; everything else (longitude wrap, spherical scaling) is
+// the same expression in the reference.
+template <int SPHERICAL, bool LINEAR = false>
 struct Spline2D {
     static constexpr int N = 2;
     static constexpr int kAux = 0;
@@ -160,7 +164,8 @@ struct Spline2D {
         if (SPHERICAL == 1) xx = pymod_pos(y[0] - 180.0, 360.0) - 180.0;
         if (SPHERICAL == 2) xx = pymod_pos(y[0], 360.0);
         double u, v;
-        eval_spline_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
+        if (LINEAR) eval_linear_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
+        else eval_spline_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
         if (SPHERICAL) {
             // ((p0*u)*180) / (pi*r*cos(yy*pi/180))   (flows.py:165-196)
             dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos_fast(yy * kPi / 180.0));

@@ -137,6 +137,37 @@ __device__ __forceinline__ double eval_spline_s(const SplineGridDev &g, const do
     return acc0;
 }
 
+// trilinear evaluation of an interleaved (u, v) field on the raw (n0, n1, n2) data: eval_linear at
+// flows.py:470-503 (get_flow_linear_2D), one 16-byte load per tap
+__device__ __forceinline__ void eval_linear_uv(const SplineGridDev &g, const double2 *__restrict__ F,
+                                               double t, double x, double y, double &u, double &v) {
+    u = 0.0;
+    v = 0.0;
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return;
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const double2 *c = F + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
+    const double m2 = 1.0 - l2;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+        const double wa = a ? l0 : 1.0 - l0;
+        double vu = 0.0, vv = 0.0;
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const double wb = b ? l1 : 1.0 - l1;
+            const double2 *cc = c + a * g.s0 + b * g.s1;
+            const double2 c0 = __ldg(cc), c1 = __ldg(cc + 1);
+            vu = fma(wb, fma(l2, c1.x, m2 * c0.x), vu);
+            vv = fma(wb, fma(l2, c1.y, m2 * c0.y), vv);
+        }
+        u = fma(wa, vu, u);
+        v = fma(wa, vv, v);
+    }
+}
+
 // scalar trilinear on the raw (n0, n1, n2) data
 __device__ __forceinline__ double eval_linear_s(const SplineGridDev &g, const double *__restrict__ F,
                                                 double t, double x, double y) {

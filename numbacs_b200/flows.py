@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["get_predefined_flow", "get_interp_arrays_2D", "get_interp_arrays_scalar",
+__all__ = ["get_predefined_flow", "get_interp_arrays_2D", "get_interp_arrays_scalar", "get_flow_linear_2D",
            "get_flow_2D", "get_callable_scalar", "get_callable_scalar_linear", "ScalarField",
            "release_flow"]
 
@@ -121,6 +121,23 @@ def get_flow_2D(grid_vel, C_eval_u, C_eval_v, spherical=0, extrap_mode="constant
     h = C.c_int(0)
     _lib.check(_lib.load().b200cs_flow_create_spline(
         C.c_void_p(g.ctypes.data), cu.ptr, cv.ptr, int(spherical), _lib.EXTRAP[extrap_mode],
+        float(r), C.byref(h)))
+    return h.value
+
+
+def get_flow_linear_2D(grid_vel, U, V, spherical=0, extrap_mode="constant", r=6371.0):
+    """Handle of the device trilinear flow over the raw velocity arrays U, V (nt, nx, ny)
+    (flows.py:418-506); same conventions as get_flow_2D."""
+    if extrap_mode not in _lib.EXTRAP:
+        raise ValueError(f"unknown extrap_mode {extrap_mode!r}")
+    g = _grid9(grid_vel)
+    ua, va = _lib.arg_in(U), _lib.arg_in(V)
+    exp = (int(g[2]), int(g[5]), int(g[8]))
+    if tuple(ua.obj.shape) != exp or tuple(va.obj.shape) != exp:
+        raise ValueError(f"velocity arrays must have shape {exp}")
+    h = C.c_int(0)
+    _lib.check(_lib.load().b200cs_flow_create_linear(
+        C.c_void_p(g.ctypes.data), ua.ptr, va.ptr, int(spherical), _lib.EXTRAP[extrap_mode],
         float(r), C.byref(h)))
     return h.value
 

@@ -53,6 +53,9 @@ def lib():
         L.oracle_flow_new_spline.restype = C.c_void_p
         L.oracle_flow_new_spline.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                              C.c_double]
+        L.oracle_flow_new_linear.restype = C.c_void_p
+        L.oracle_flow_new_linear.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_double]
         L.oracle_scalar_new.restype = C.c_void_p
         L.oracle_scalar_new.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_free.argtypes = [C.c_void_p]
@@ -225,6 +228,14 @@ def get_flow_2D(grid_vel, C_eval_u, C_eval_v, spherical=0, extrap_mode="constant
     h = lib().oracle_flow_new_spline(_ptr(g), _ptr(cu), _ptr(cv), int(spherical),
                                      EXTRAP[extrap_mode], float(r))
     return Flow(h, 2, keep=(g, cu, cv))
+
+
+def get_flow_linear_2D(grid_vel, U, V, spherical=0, extrap_mode="constant", r=6371.0):
+    g = _grid9(grid_vel)
+    u, v = _f64(U), _f64(V)
+    h = lib().oracle_flow_new_linear(_ptr(g), _ptr(u), _ptr(v), int(spherical), EXTRAP[extrap_mode],
+                                     float(r))
+    return Flow(h, 2, keep=(g, u, v))
 
 
 def get_callable_scalar(grid_f, C_eval_f, extrap_mode="constant"):

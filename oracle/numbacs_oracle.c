@@ -48,7 +48,7 @@
 
 #define MAXN 3
 
-enum { FLOW_DOUBLE_GYRE = 0, FLOW_BICKLEY_JET = 1, FLOW_ABC = 2, FLOW_SPLINE2D = 3 };
+enum { FLOW_DOUBLE_GYRE = 0, FLOW_BICKLEY_JET = 1, FLOW_ABC = 2, FLOW_SPLINE2D = 3, FLOW_LINEAR2D = 4 };
 enum { EXTRAP_CONSTANT = 0, EXTRAP_LINEAR = 1, EXTRAP_NEAREST = 2 };
 
 /* ------------------------------------------------------------------ spline ------------- */
@@ -282,13 +282,20 @@ static void rhs_eval(const flow_t *f, double t, const double *y, double *dy, con
         dy[2] = p[0] * (p[3] * sin(y[1]) + p[2] * cos(y[1]));
         break;
     }
-    case FLOW_SPLINE2D: { /* flows.py:156-253 */
+    case FLOW_SPLINE2D:   /* flows.py:156-253 */
+    case FLOW_LINEAR2D: { /* flows.py:458-503: same expressions with eval_linear on the raw data */
         double tt = p[0] * t;
         double xx = y[0], yy = y[1];
         if (f->spherical == 1) xx = pymod(y[0] - 180, 360) - 180;
         else if (f->spherical == 2) xx = pymod(y[0], 360);
-        double u = oracle_eval_spline3(&f->u, tt, xx, yy);
-        double v = oracle_eval_spline3(&f->v, tt, xx, yy);
+        double u, v;
+        if (f->kind == FLOW_LINEAR2D) {
+            u = oracle_eval_linear3(&f->u, tt, xx, yy);
+            v = oracle_eval_linear3(&f->v, tt, xx, yy);
+        } else {
+            u = oracle_eval_spline3(&f->u, tt, xx, yy);
+            v = oracle_eval_spline3(&f->v, tt, xx, yy);
+        }
         if (f->spherical) {
             dy[0] = ((p[0] * u) * 180) / (pi * f->r * cos(yy * pi / 180));
             dy[1] = ((p[0] * v) * 180) / (pi * f->r);
@@ -963,6 +970,15 @@ flow_t *oracle_flow_new_spline(const double *grid9, const double *Cu, const doub
     f->r = r;
     fill_spline(&f->u, grid9, Cu, extrap);
     fill_spline(&f->v, grid9, Cv, extrap);
+    return f;
+}
+
+/* get_flow_linear_2D (flows.py:418-506): raw (nt, nx, ny) arrays, trilinear */
+flow_t *oracle_flow_new_linear(const double *grid9, const double *U, const double *V, int spherical,
+                               int extrap, double r)
+{
+    flow_t *f = oracle_flow_new_spline(grid9, U, V, spherical, extrap, r);
+    f->kind = FLOW_LINEAR2D;
     return f;
 }
 

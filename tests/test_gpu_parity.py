@@ -551,3 +551,66 @@ def test_pipelined_host_path_equals_device_path(nb):
                                                      halo=(1, 1))
     _, ft_full = nb.diagnostics.flowmap_ftle_grid_2D(f, 0.0, -4.0, x, y, p, dx, dy, return_flowmap=False)
     assert np.array_equal(ft_halo, ft_full[301:2499])
+
+
+# ------------------------------------------------------------------ trilinear gridded flow
+
+def test_linear_flow(nb, lib, oracle, golden):
+    """get_flow_linear_2D (flows.py:418-506): RHS against the reference's eval_linear table
+    (tests/test_flows.py:208-285) and the oracle, flow maps against the oracle.  A trilinear
+    velocity has kinks at every cell face, where the step controller rejects and the accept /
+    reject sequence is sensitive to rounding, so the flow-map gate is calibrated against the
+    oracle's own one-ulp sensitivity like the spline tests."""
+    # (1) the reference's literal table through the RHS entry point
+    t3 = np.array([0.0, 0.1, 0.2])
+    x3 = np.array([0.0, 0.5, 1.0])
+    T, X, Y = np.meshgrid(t3, x3, x3, indexing="ij")
+    u = np.sin(X) * np.cos(Y) + np.sin(T)
+    v = np.cos(X) * np.sin(Y) + np.cos(T)
+    grid3 = ((0.0, 0.2, 3), (0.0, 1.0, 3), (0.0, 1.0, 3))
+    h = nb.flows.get_flow_linear_2D(grid3, u, v)
+    xi = np.array([0.1, 0.4, 0.7])
+    Ti, Xi, Yi = np.meshgrid(np.array([0.05, 0.12, 0.18]), xi, xi, indexing="ij")
+    vel = _gpu_rhs(lib, h, Ti.ravel(), np.column_stack((Xi.ravel(), Yi.ravel())), np.array([1.0]))
+    assert np.allclose(vel[:, 0], golden["linear_eval_u"]) and np.allclose(vel[:, 1], golden["linear_eval_v"])
+    # (2) RHS vs oracle incl. the three extrapolation modes and points outside the grid
+    t, x, y, U, V = _dg_like_field()
+    grid = ((t[0], t[-1], len(t)), (x[0], x[-1], len(x)), (y[0], y[-1], len(y)))
+    rng = np.random.default_rng(9)
+    pts = rng.uniform((-0.2, -0.1), (2.2, 1.1), size=(3000, 2))
+    ts = rng.uniform(-1, 11, size=3000)
+    for mode in ("constant", "linear", "nearest"):
+        f = nb.flows.get_flow_linear_2D(grid, U, V, extrap_mode=mode)
+        fo = oracle.get_flow_linear_2D(grid, U, V, extrap_mode=mode)
+        for p0 in (1.0, -1.0):
+            g = _gpu_rhs(lib, f, p0 * ts, pts, np.array([p0]))
+            o = np.array([fo.rhs(p0 * ts[i], pts[i], np.array([p0])) for i in range(len(ts))])
+            assert np.abs(g - o).max() <= 1e-14
+    # (3) flow maps
+    f = nb.flows.get_flow_linear_2D(grid, U, V)
+    fo = oracle.get_flow_linear_2D(grid, U, V)
+    xg, yg = np.linspace(0.05, 1.95, 101), np.linspace(0.05, 0.95, 51)
+    params = np.array([1.0])
+    info = {}
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, xg, yg, params, info=info)
+    fmo, _, st_o, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 8.0, xg, yg, params, full=True)
+    assert (info["status"] == 1).all() and (st_o == 1).all()
+    r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
+    fo2 = oracle.get_flow_linear_2D(grid, U * (1 + 2.3e-16), V)
+    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 8.0, xg, yg, params, (2.0, 1.0), flow_o2=fo2)
+    assert r["median"] <= 1e-12 and r["p99"] <= max(1e-9, 20 * floor), (r, floor)
+    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
+    assert r["mismatch"] <= max(2, 5 * floor_mis), (r, floor_mis)
+    # spherical variant shares the expressions of the spline flow (flows.py:458-491)
+    lon, lat = -180.0 + 5.0 * np.arange(72), -90.0 + 5.0 * np.arange(37)
+    tt = np.arange(13) * 1.0
+    Tm, LO, LA = np.meshgrid(tt, np.deg2rad(lon), np.deg2rad(lat), indexing="ij")
+    Us, Vs = 40.0 * np.cos(LA) * np.sin(2 * LO + 0.1 * Tm), 25.0 * np.cos(LA) * np.cos(LO - 0.1 * Tm)
+    gs = ((tt[0], tt[-1], 13), (lon[0], lon[-1], 72), (lat[0], lat[-1], 37))
+    fs = nb.flows.get_flow_linear_2D(gs, Us, Vs, spherical=1, extrap_mode="linear")
+    fso = oracle.get_flow_linear_2D(gs, Us, Vs, spherical=1, extrap_mode="linear")
+    q = rng.uniform((-400.0, -60.0), (400.0, 60.0), size=(2000, 2))   # incl. longitudes that wrap
+    tq = rng.uniform(0, 12, size=2000)
+    g = _gpu_rhs(lib, fs, -tq, q, np.array([-1.0]))
+    o = np.array([fso.rhs(-tq[i], q[i], np.array([-1.0])) for i in range(len(tq))])
+    assert np.abs(g - o).max() <= 1e-13 * np.abs(o).max()
