@@ -586,7 +586,11 @@ def test_linear_flow(nb, lib, oracle, golden):
             g = _gpu_rhs(lib, f, p0 * ts, pts, np.array([p0]))
             o = np.array([fo.rhs(p0 * ts[i], pts[i], np.array([p0])) for i in range(len(ts))])
             assert np.abs(g - o).max() <= 1e-14
-    # (3) flow maps
+    # (3) flow maps.  With a piecewise-linear velocity the step sequence of practically every
+    # particle is decided by rounding noise (measured: a one-ulp change of U changes 99 % of the
+    # oracle's own step sequences and moves its particles by up to 5e-5 = the solver's truncation
+    # error at rtol 1e-6), so no implementation can match another beyond that level; the GPU must
+    # differ from the oracle by no more than the oracle differs from itself.
     f = nb.flows.get_flow_linear_2D(grid, U, V)
     fo = oracle.get_flow_linear_2D(grid, U, V)
     xg, yg = np.linspace(0.05, 1.95, 101), np.linspace(0.05, 0.95, 51)
@@ -595,12 +599,24 @@ def test_linear_flow(nb, lib, oracle, golden):
     fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, xg, yg, params, info=info)
     fmo, _, st_o, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 8.0, xg, yg, params, full=True)
     assert (info["status"] == 1).all() and (st_o == 1).all()
-    r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
     fo2 = oracle.get_flow_linear_2D(grid, U * (1 + 2.3e-16), V)
-    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 8.0, xg, yg, params, (2.0, 1.0), flow_o2=fo2)
-    assert r["median"] <= 1e-12 and r["p99"] <= max(1e-9, 20 * floor), (r, floor)
-    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
-    assert r["mismatch"] <= max(2, 5 * floor_mis), (r, floor_mis)
+    fmo2 = oracle.flowmap_grid_2D(fo2, 0.0, 8.0, xg, yg, params)
+    L = np.array([2.0, 1.0])
+    d_gpu = (np.abs(fm - fmo) / L).max(-1)
+    d_self = (np.abs(fmo2 - fmo) / L).max(-1)
+    for q in (50, 90, 99):
+        assert np.percentile(d_gpu, q) <= 3 * np.percentile(d_self, q) + 1e-12, (q, np.percentile(d_gpu, q))
+    assert d_gpu.max() <= 10 * d_self.max()
+    # with tight tolerances both the self-sensitivity and the GPU-oracle distance drop by ~1e3
+    tight = dict(rtol=1e-10, atol=1e-12)
+    fm_t = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, xg, yg, params, **tight)
+    fmo_t = oracle.flowmap_grid_2D(fo, 0.0, 8.0, xg, yg, params, **tight)
+    fmo2_t = oracle.flowmap_grid_2D(fo2, 0.0, 8.0, xg, yg, params, **tight)
+    d_gpu_t = (np.abs(fm_t - fmo_t) / L).max(-1)
+    d_self_t = (np.abs(fmo2_t - fmo_t) / L).max(-1)
+    for q in (50, 90, 99):
+        assert np.percentile(d_gpu_t, q) <= 3 * np.percentile(d_self_t, q) + 1e-12, (q, np.percentile(d_gpu_t, q))
+    assert np.median(d_gpu_t) <= 1e-2 * np.median(d_gpu) + 1e-12
     # spherical variant shares the expressions of the spline flow (flows.py:458-491)
     lon, lat = -180.0 + 5.0 * np.arange(72), -90.0 + 5.0 * np.arange(37)
     tt = np.arange(13) * 1.0
