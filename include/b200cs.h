@@ -277,6 +277,11 @@ B200CS_API int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, 
 B200CS_API int b200cs_flowmap_composition(const double *flowmaps, const double *grid6, int64_t nT,
                                double *composed, void *stream);
 
+/* binary_mask_dilation(mask, corners)          (utils.py:1923-1985)
+ * dilated[i, j] = mask[i, j] or any of its 4 (corners != 0: 8) neighbours; bytes (numpy bool_). */
+B200CS_API int b200cs_binary_mask_dilation(const uint8_t *mask, int64_t nx, int64_t ny, int corners,
+                                uint8_t *dilated, void *stream);
+
 /* out2 = { sorted(data)[k], sorted(data)[min(k+1, n-1)] } by radix select (no sort, data is not
  * modified): the two order statistics np.percentile interpolates between (ridges.py:45, 279). */
 B200CS_API int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream);

@@ -12,7 +12,7 @@ Drop-in for the reference's hot-path API (same function names, arguments and arr
 Python only marshals pointers: all arithmetic runs in hand-written sm_100a CUDA kernels behind the
 C-ABI of libb200cs.so (include/b200cs.h).  There is no CPU fallback.
 """
-from . import _lib, diagnostics, extraction, flows, integration  # noqa: F401
+from . import _lib, diagnostics, extraction, flows, integration, utils  # noqa: F401
 
 __version__ = "0.1.0"
 
@@ -22,5 +22,5 @@ def install_as_numbacs():
     unmodified reference script picks up the GPU path."""
     import sys
     sys.modules.setdefault("numbacs", sys.modules[__name__])
-    for sub in ("flows", "integration", "diagnostics", "extraction"):
+    for sub in ("flows", "integration", "diagnostics", "extraction", "utils"):
         sys.modules.setdefault("numbacs." + sub, sys.modules[__name__ + "." + sub])

@@ -58,6 +58,7 @@ PROTOTYPES = {
                               _i64, _vp, _vp],
     "b200cs_ftle_ridges": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _vp, _vp, _i64, _vp, _vp],
     "b200cs_flowmap_composition": [_vp, _vp, _i64, _vp, _vp],
+    "b200cs_binary_mask_dilation": [_vp, _i64, _i64, _i, _vp, _vp],
     "b200cs_order_stats": [_vp, _i64, _i64, _vp, _vp],
     "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
 }
@@ -171,7 +172,8 @@ def alloc_out(shape, dtype, device):
     """Output buffer: numpy (host) or torch CUDA tensor (device)."""
     if device:
         import torch
-        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64}[dtype]
+        tdt = {np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64,
+               np.bool_: torch.bool}[dtype]
         t = torch.empty(shape, dtype=tdt, device="cuda")
         return Arg(t, C.c_void_p(t.data_ptr()), True)
     arr = np.empty(shape, dtype=dtype)

@@ -931,6 +931,24 @@ int b200cs_flowmap_composition(const double *flowmaps, const double *grid6, int6
     });
 }
 
+int b200cs_binary_mask_dilation(const uint8_t *mask, int64_t nx, int64_t ny, int corners, uint8_t *dilated,
+                                void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(mask && dilated, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<uint8_t> din(mask, np, s);
+        Out<uint8_t> dout(dilated, np, s);
+        B2_REQUIRE(din.dev != dout.dev, "in-place dilation is not supported");
+        launch_mask_dilation(din.dev, nx, ny, corners != 0, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream) {
     return guarded([&] {
         require_device();

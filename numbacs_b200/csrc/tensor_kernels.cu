@@ -475,6 +475,23 @@ composition_kernel(const double2 *__restrict__ fms, const __grid_constant__ Grid
     out[q] = bilinear2(g, fms + (nT - 1) * np, p.x, p.y);
 }
 
+// ---- binary_mask_dilation (utils.py:1923-1985) ----------------------------------------------------
+// one byte per pixel: a pixel is set when it or one of its 4 (corners: 8) neighbours is set
+__global__ void __launch_bounds__(kTB)
+mask_dilation_kernel(const uint8_t *__restrict__ mask, long long nx, long long ny, int corners,
+                     uint8_t *__restrict__ out) {
+    const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
+    if (q >= nx * ny) return;
+    const long long i = q / ny, j = q - i * ny;
+    const bool up = i > 0, dn = i < nx - 1, lf = j > 0, rt = j < ny - 1;
+    bool v = mask[q] != 0;
+    v = v || (up && mask[q - ny]) || (dn && mask[q + ny]) || (lf && mask[q - 1]) || (rt && mask[q + 1]);
+    if (corners)
+        v = v || (up && lf && mask[q - ny - 1]) || (up && rt && mask[q - ny + 1]) ||
+            (dn && lf && mask[q + ny - 1]) || (dn && rt && mask[q + ny + 1]);
+    out[q] = v ? 1 : 0;
+}
+
 // ---- order statistics: sorted(data)[k] and sorted(data)[k+1] by MSB-first radix select ----------
 struct SelectState {
     unsigned long long prefix, mask;  // key bits fixed so far
@@ -684,6 +701,12 @@ void launch_composition(const double *flowmaps, const double *grid6, long long n
     }
     composition_kernel<<<blocks_for((long long)g.n[0] * g.n[1]), kTB, 0, s>>>(
         reinterpret_cast<const double2 *>(flowmaps), g, nT, reinterpret_cast<double2 *>(out));
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_mask_dilation(const uint8_t *mask, long long nx, long long ny, bool corners, uint8_t *out,
+                          cudaStream_t s) {
+    mask_dilation_kernel<<<blocks_for(nx * ny), kTB, 0, s>>>(mask, nx, ny, corners ? 1 : 0, out);
     B2_CHECK_CUDA(cudaGetLastError());
 }
 

@@ -458,3 +458,19 @@ def flowmap_composition_step(flowmaps, flow, t0, h, nT, x, y, grid, params, **kw
     flowmaps[:-1] = flowmaps[1:].copy()
     flowmaps[-1] = flowmap_grid_2D(flow, t0, h, x, y, params, **kwargs)
     return flowmap_composition(flowmaps, grid, nT), flowmaps
+
+
+def binary_mask_dilation(mask, corners=False):
+    """binary_mask_dilation (utils.py:1923-1985), restated with shifted views."""
+    m = np.asarray(mask, dtype=bool)
+    out = m.copy()
+    out[1:] |= m[:-1]
+    out[:-1] |= m[1:]
+    out[:, 1:] |= m[:, :-1]
+    out[:, :-1] |= m[:, 1:]
+    if corners:
+        out[1:, 1:] |= m[:-1, :-1]
+        out[1:, :-1] |= m[:-1, 1:]
+        out[:-1, 1:] |= m[1:, :-1]
+        out[:-1, :-1] |= m[1:, 1:]
+    return out

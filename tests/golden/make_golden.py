@@ -143,6 +143,14 @@ def main():
         G["ridges_len_" + tag] = np.array([len(r) for r in rr])
     G["ridges_args"] = np.array([[0.0, 0, 3], [10.0, 60, 1]])
 
+    # (5) mask dilation: the real numbacs.utils.binary_mask_dilation on a seeded mask
+    from numbacs.utils import binary_mask_dilation
+    mk = rng.random((37, 29)) < 0.08
+    mk[0, 0] = mk[-1, -1] = mk[0, 13] = mk[20, -1] = True
+    G["dil_in"] = mk
+    G["dil_out4"] = binary_mask_dilation(mk)
+    G["dil_out8"] = binary_mask_dilation(mk, corners=True)
+
     out = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(out, **G)
     print("wrote", out, os.path.getsize(out), "bytes;", len(G), "arrays")

@@ -309,3 +309,40 @@ def test_flowmap_composition_vs_oracle_device_resident(nb, oracle):
     fms[0, 5, 7, 0] = 2.5
     out = I.flowmap_composition(fms, grid, nT)
     assert not out[5, 7].any()
+
+
+# ------------------------------------------------------------------ mask helpers
+
+def test_mask_helpers(nb, golden, oracle):
+    import torch
+    U = nb.utils
+    m = golden["dil_in"]
+    d4, d8 = U.binary_mask_dilation(m), U.binary_mask_dilation(m, corners=True)
+    assert d4.dtype == np.bool_ and np.array_equal(d4, golden["dil_out4"]) and np.array_equal(d8, golden["dil_out8"])
+    md = torch.from_numpy(m).cuda()
+    assert torch.equal(U.binary_mask_dilation(md, corners=True).cpu(), torch.from_numpy(golden["dil_out8"]))
+    rng = np.random.default_rng(2)
+    big = rng.random((515, 1027)) < 0.01
+    assert np.array_equal(U.binary_mask_dilation(big), oracle.binary_mask_dilation(big))
+    for shape in ((1, 7), (7, 1), (1, 1)):
+        one = np.zeros(shape, bool)
+        one[0, 0] = True
+        assert np.array_equal(U.binary_mask_dilation(one, corners=True), oracle.binary_mask_dilation(one, True))
+    # fill_nans_and_get_mask: in place, mask from the first time slice
+    u = rng.normal(size=(3, 5, 4))
+    v = rng.normal(size=(3, 5, 4))
+    u[:, 1, 2] = np.nan
+    v[:, 1, 2] = np.nan
+    u2, v2, mask = U.fill_nans_and_get_mask((u, v))
+    assert u2 is u and mask.shape == (5, 4) and mask.sum() == 1 and mask[1, 2]
+    assert not np.isnan(u).any() and (u[:, 1, 2] == 0).all() and (v[:, 1, 2] == 0).all()
+    # the dilated mask keeps the C_eig stencil away from masked flow-map entries
+    x, y = np.linspace(0, 2, 41), np.linspace(0, 1, 21)
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    hole = np.zeros((41, 21), bool)
+    hole[10:13, 5:8] = True
+    fm = nb.integration.flowmap_grid_2D(f, 0.0, 5.0, x, y, p, mask=hole)
+    vals, _ = nb.diagnostics.C_eig_2D(fm, x[1], y[1], U.binary_mask_dilation(hole))
+    ref, _ = nb.diagnostics.C_eig_2D(nb.integration.flowmap_grid_2D(f, 0.0, 5.0, x, y, p), x[1], y[1])
+    keep = ~U.binary_mask_dilation(hole)
+    assert np.array_equal(vals[keep], ref[keep]) and not vals[~keep].any()

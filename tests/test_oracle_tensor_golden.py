@@ -190,3 +190,8 @@ def test_flowmap_composition_golden(oracle, golden, coords_dg):
     assert not out[3, 4].any() and not out[5, 6].any()
     assert np.array_equal(np.delete(out.reshape(-1, 2), [3 * 11 + 4, 5 * 11 + 6], axis=0),
                           np.delete(fm0.reshape(-1, 2), [3 * 11 + 4, 5 * 11 + 6], axis=0))
+
+
+def test_binary_mask_dilation_matches_real_reference(oracle, golden):
+    assert np.array_equal(oracle.binary_mask_dilation(golden["dil_in"]), golden["dil_out4"])
+    assert np.array_equal(oracle.binary_mask_dilation(golden["dil_in"], corners=True), golden["dil_out8"])
