@@ -244,7 +244,9 @@ B200CS_API int b200cs_ftle_from_eig(const double *eigval_max, int64_t n, int64_t
 /* ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh, percentile)          (extraction/ridges.py:9-76)
  * _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)  (ridges.py:232-318)
  * eigvec_max[i, j, c] is read at eigvec_max[(i*ny + j)*ev_pixel_stride + c*ev_comp_stride] so that
- * eigvecs[:, :, :, 1] (strides 4, 2) can be passed in place.  f_min = 0 or np.percentile(f, p)
+ * eigvecs[:, :, :, 1] (strides 4, 2) can be passed in place.  dx, dy are the reference's
+ * x[1] - x[0], y[1] - y[0] (ridges.py:39-40), passed explicitly so that a row slab of a larger
+ * grid uses the spacing of the full grid.  f_min = 0 or np.percentile(f, p)
  * (from b200cs_order_stats).  All outputs are nullable:
  *   r_pts [nx*ny, 3], r_vec [nx*ny, 2], sdd [nx*ny]  per-pixel arrays of the _connect form
  *       (r_pts rows are -1 where there is no ridge point, the third column is the reference's
@@ -254,7 +256,8 @@ B200CS_API int b200cs_ftle_from_eig(const double *eigval_max, int64_t n, int64_t
  *       capacity (call with pts_compact = NULL first to size the buffer). */
 B200CS_API int b200cs_ftle_ridge_pts(const double *ftle /*[nx,ny]*/, const double *eigvec_max,
                           int64_t ev_pixel_stride, int64_t ev_comp_stride, int64_t nx, int64_t ny,
-                          const double *x, const double *y, double sdd_thresh, double f_min,
+                          const double *x, const double *y, double dx, double dy,
+                          double sdd_thresh, double f_min,
                           double *r_pts, double *r_vec, double *sdd, double *pts_compact,
                           int64_t capacity, int64_t *count, void *stream);
 
@@ -265,7 +268,8 @@ B200CS_API int b200cs_ftle_ridge_pts(const double *ftle /*[nx,ny]*/, const doubl
  * Points come in raveled-pixel order; grouping them by root gives the reference's list of ridges. */
 B200CS_API int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
                        int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
-                       double sdd_thresh, double f_min, double *pts_compact /*[capacity,2]*/,
+                       double dx, double dy, double sdd_thresh, double f_min,
+                       double *pts_compact /*[capacity,2]*/,
                        int64_t *roots_compact /*[capacity]*/, int64_t capacity, int64_t *count,
                        void *stream);
 

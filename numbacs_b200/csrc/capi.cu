@@ -796,7 +796,7 @@ int b200cs_ftle_from_eig(const double *eigval_max, int64_t n, int64_t stride, do
 
 int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
                           int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
-                          double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
+                          double dx, double dy, double sdd_thresh, double f_min, double *r_pts, double *r_vec, double *sdd,
                           double *pts_compact, int64_t capacity, int64_t *count, void *stream) {
     return guarded([&] {
         require_device();
@@ -809,10 +809,7 @@ int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t 
         const size_t np = (size_t)nx * ny;
         In<double> df(ftle, np, s);
         In<double> dev(eigvec_max, (np - 1) * ev_pixel_stride + ev_comp_stride + 1, s);
-        // dx = x[1] - x[0], dy = y[1] - y[0] (ridges.py:39-40) are taken on the host
-        double x01[2], y01[2];
-        B2_CHECK_CUDA(cudaMemcpy(x01, x, sizeof(x01), cudaMemcpyDefault));
-        B2_CHECK_CUDA(cudaMemcpy(y01, y, sizeof(y01), cudaMemcpyDefault));
+        B2_REQUIRE(dx != 0.0 && dy != 0.0, "dx and dy must be non-zero");
         In<double> dxs(x, nx, s), dys(y, ny, s);
         Out<double> drp(r_pts, np * 3, s), drv(r_vec, np * 2, s), dsdd(sdd, np, s);
         // compact output: a host buffer only receives the rows that were found
@@ -834,7 +831,7 @@ int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t 
             }
         }
         launch_ridge_pts(df.dev, dev.dev, ev_pixel_stride, ev_comp_stride, nx, ny, dxs.dev, dys.dev,
-                         x01[1] - x01[0], y01[1] - y01[0], sdd_thresh, f_min, drp.dev, drv.dev, dsdd.dev,
+                         dx, dy, sdd_thresh, f_min, drp.dev, drv.dev, dsdd.dev,
                          capacity > 0 ? cp_dev : nullptr, capacity, cnt_dev, s);
         drp.download();
         drv.download();
@@ -856,7 +853,7 @@ int b200cs_ftle_ridge_pts(const double *ftle, const double *eigvec_max, int64_t 
 
 int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_pixel_stride,
                        int64_t ev_comp_stride, int64_t nx, int64_t ny, const double *x, const double *y,
-                       double sdd_thresh, double f_min, double *pts_compact, int64_t *roots_compact,
+                       double dx, double dy, double sdd_thresh, double f_min, double *pts_compact, int64_t *roots_compact,
                        int64_t capacity, int64_t *count, void *stream) {
     return guarded([&] {
         require_device();
@@ -868,9 +865,7 @@ int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_
         const size_t np = (size_t)nx * ny;
         In<double> df(ftle, np, s);
         In<double> dev(eigvec_max, (np - 1) * ev_pixel_stride + ev_comp_stride + 1, s);
-        double x01[2], y01[2];
-        B2_CHECK_CUDA(cudaMemcpy(x01, x, sizeof(x01), cudaMemcpyDefault));
-        B2_CHECK_CUDA(cudaMemcpy(y01, y, sizeof(y01), cudaMemcpyDefault));
+        B2_REQUIRE(dx != 0.0 && dy != 0.0, "dx and dy must be non-zero");
         In<double> dxs(x, nx, s), dys(y, ny, s);
         const bool host_out = capacity > 0 && !is_device_ptr(pts_compact);
         B2_REQUIRE(capacity == 0 || host_out == !is_device_ptr(roots_compact),
@@ -891,7 +886,7 @@ int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_
             cnt_dev = static_cast<long long *>(cnt_tmp.ptr);
         }
         launch_ridge_components(df.dev, dev.dev, ev_pixel_stride, ev_comp_stride, nx, ny, dxs.dev, dys.dev,
-                                x01[1] - x01[0], y01[1] - y01[0], sdd_thresh, f_min, cp_dev, rt_dev, capacity,
+                                dx, dy, sdd_thresh, f_min, cp_dev, rt_dev, capacity,
                                 cnt_dev, s);
         if (cnt_host || host_out) {
             long long found = 0;

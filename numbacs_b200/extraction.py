@@ -64,7 +64,14 @@ def _eigvec_in(eigvec_max, nx, ny):
     return _lib.arg_in(a), 2, 1
 
 
-def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
+def _spacing(xa, ya, spacing):
+    """dx = x[1] - x[0], dy = y[1] - y[0] (ridges.py:39-40) unless given (row slabs of a larger grid)."""
+    if spacing is not None:
+        return float(spacing[0]), float(spacing[1])
+    return float(xa.obj[1] - xa.obj[0]), float(ya.obj[1] - ya.obj[0])
+
+
+def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out, spacing=None):
     fa, xa, ya = _lib.arg_in(f), _lib.arg_in(x), _lib.arg_in(y)
     if fa.obj.ndim != 2:
         raise ValueError("f must have shape (nx, ny)")
@@ -73,6 +80,7 @@ def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
         raise ValueError("the grid needs at least 2 points per axis")
     ev, ps, cs = _eigvec_in(eigvec_max, nx, ny)
     f_min = 0.0 if percentile == 0 else percentile_value(fa.obj, percentile)
+    dx, dy = _spacing(xa, ya, spacing)
     dev = bool(device_out or fa.on_device)
     L = _lib.load()
     stream = _lib.current_stream(dev)
@@ -82,7 +90,7 @@ def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
         r_pts = _lib.alloc_out((nx * ny, 3), np.float64, dev)
         r_vec = _lib.alloc_out((nx * ny, 2), np.float64, dev)
         sdd = _lib.alloc_out((nx * ny,), np.float64, dev)
-        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr, dx, dy,
                                            float(sdd_thresh), f_min, r_pts.ptr, r_vec.ptr, sdd.ptr,
                                            None, 0, None, stream))
         return r_pts.obj, r_vec.obj, sdd.obj
@@ -91,7 +99,7 @@ def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
     cap = max(4096, (nx * ny) // 32)
     for _ in range(2):
         pts = _lib.alloc_out((cap, 2), np.float64, dev)
-        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+        _lib.check(L.b200cs_ftle_ridge_pts(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr, dx, dy,
                                            float(sdd_thresh), f_min, None, None, None, pts.ptr, cap,
                                            cptr, stream))
         n = int(count[0])
@@ -101,9 +109,10 @@ def _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, full, device_out):
     return pts.obj[:n].clone() if dev else pts.obj[:n].copy()
 
 
-def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *, device_out=False):
-    """Sub-pixel FTLE ridge points -> (k, 2), in raveled pixel order."""
-    return _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, False, device_out)
+def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *, device_out=False, spacing=None):
+    """Sub-pixel FTLE ridge points -> (k, 2), in raveled pixel order.  `spacing` = (dx, dy)
+    overrides x[1] - x[0], y[1] - y[0] (used for row slabs of a larger grid)."""
+    return _ridge_call(f, eigvec_max, x, y, sdd_thresh, percentile, False, device_out, spacing)
 
 
 def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, *, device_out=False):
@@ -125,6 +134,7 @@ def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts
     nx, ny = int(fa.obj.shape[0]), int(fa.obj.shape[1])
     ev, ps, cs = _eigvec_in(eigvec_max, nx, ny)
     f_min = 0.0 if percentile == 0 else percentile_value(fa.obj, percentile)
+    dx, dy = _spacing(xa, ya, None)
     L = _lib.load()
     stream = _lib.current_stream(fa.on_device)
     count = np.zeros(1, np.int64)
@@ -132,7 +142,7 @@ def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts
     for _ in range(2):
         pts = np.empty((cap, 2), np.float64)
         roots = np.empty(cap, np.int64)
-        _lib.check(L.b200cs_ftle_ridges(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr,
+        _lib.check(L.b200cs_ftle_ridges(fa.ptr, ev.ptr, ps, cs, nx, ny, xa.ptr, ya.ptr, dx, dy,
                                         float(sdd_thresh), f_min, C.c_void_p(pts.ctypes.data),
                                         C.c_void_p(roots.ctypes.data), cap,
                                         C.c_void_p(count.ctypes.data), stream))

@@ -7,13 +7,15 @@ communication at all.  The FTLE stencil needs the flow map at rows i-1 / i+1
 (/root/reference/src/numbacs/utils.py:41-44): each rank sends its first / last flow-map row
 (ny x 2 float64 = 262 KB at ny = 16384) to its lower / upper neighbour -- one point-to-point
 exchange, the only data-path collective -- and an optional gather assembles the result on rank 0.
+The ridge tail of config 5 (Cauchy-Green eigen-pairs -> FTLE -> ridge points) widens the halo to
+two rows and is otherwise local (flowmap_ridges_sharded).
 
 Spline coefficient arrays are replicated: every rank creates its own flow handle.
 """
 import numpy as np
 
 __all__ = ["row_block", "balanced_row_blocks", "estimate_row_cost", "exchange_halo_rows",
-           "flowmap_ftle_sharded", "gather_rows"]
+           "flowmap_ftle_sharded", "flowmap_ridges_sharded", "gather_rows", "gather_points"]
 
 
 def row_block(nx, world_size, rank):
@@ -60,18 +62,21 @@ def estimate_row_cost(funcptr, t0, T, x, y, params, rtol=1e-6, atol=1e-8, rows=2
     return np.interp(np.arange(nx), ix, per_row)
 
 
-def exchange_halo_rows(slab, has_lo, has_hi, rank, group=None):
-    """slab[(has_lo + rows + has_hi), ny, 2] with the owned rows already in place: sends the first
-    / last OWNED row to rank-1 / rank+1 and receives their edge rows into slab[0] / slab[-1].
-    Works on CUDA tensors (NCCL) and CPU tensors (gloo)."""
+def exchange_halo_rows(slab, has_lo, has_hi, rank, group=None, width=1):
+    """slab[(w*has_lo + rows + w*has_hi), ny, 2] with the owned rows already in place: sends the
+    first / last `width` OWNED rows to rank-1 / rank+1 and receives their edge rows into
+    slab[:w] / slab[-w:].  width = 1 for the FTLE stencil, 2 for the ridge tail (the ridge stencil
+    reads FTLE at i +- 1, which reads the flow map at i +- 2).  Works on CUDA tensors (NCCL) and
+    CPU tensors (gloo)."""
     import torch.distributed as dist
+    w = int(width)
     ops = []
     if has_lo:
-        ops.append(dist.P2POp(dist.isend, slab[1], rank - 1, group))
-        ops.append(dist.P2POp(dist.irecv, slab[0], rank - 1, group))
+        ops.append(dist.P2POp(dist.isend, slab[w:2 * w], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, slab[:w], rank - 1, group))
     if has_hi:
-        ops.append(dist.P2POp(dist.isend, slab[-2], rank + 1, group))
-        ops.append(dist.P2POp(dist.irecv, slab[-1], rank + 1, group))
+        ops.append(dist.P2POp(dist.isend, slab[-2 * w:-w] if w > 0 else slab[:0], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, slab[-w:], rank + 1, group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
@@ -132,6 +137,85 @@ def flowmap_ftle_sharded(funcptr, t0, T, x, y, params, dx, dy, method="dop853", 
         exchange_halo_rows(slab, has_lo, has_hi, rank, group)
     ft = ftle(slab, T, dx, dy, (has_lo, has_hi)) if rows else torch.empty((0, ny), dtype=torch.float64, device=device)
     return own, ft, (i0, i1)
+
+
+def _cuda_ridge_backend():
+    from .diagnostics import C_eig_2D, ftle_from_eig
+    from .extraction import ftle_ridge_pts
+
+    def ridge_tail(slab, T, dx, dy, x_slab, y, sdd_thresh):
+        vals, vecs = C_eig_2D(slab, dx, dy)
+        ftle = ftle_from_eig(vals[:, :, 1], T)
+        return ftle, ftle_ridge_pts(ftle, vecs[:, :, :, 1], x_slab, y, sdd_thresh=sdd_thresh, percentile=0,
+                                    spacing=(dx, dy))
+
+    return ridge_tail
+
+
+def flowmap_ridges_sharded(funcptr, t0, T, x, y, params, dx, dy, sdd_thresh=0.0, method="dop853",
+                           rtol=1e-6, atol=1e-8, *, group=None, backend=None, ridge_backend=None,
+                           info=None, blocks=None):
+    """Config 5 end to end on row blocks: each rank integrates its rows, exchanges TWO flow-map
+    rows with each neighbour, and runs C_eig_2D -> ftle_from_eig -> ftle_ridge_pts on its slab.
+
+    The ridge test at row i reads the FTLE field at i +- 1 and that reads the flow map at i +- 2,
+    so with a two-row halo the whole tail is local; the ridge kernel's own border rule (rows
+    2 .. m-3 of what it is given) then selects exactly the rows a rank owns (and, on the first /
+    last rank, drops the two global border rows like the reference).  Ridge points of consecutive
+    ranks concatenate to the single-process result (raveled pixel order).  percentile is fixed at
+    0 (the example's setting): a global percentile would need a distributed selection.
+
+    Returns (flowmap_block [rows, ny, 2], ftle_block [rows, ny], ridge_pts [k, 2], (i0, i1))."""
+    import torch
+    import torch.distributed as dist
+    if method.lower() != "dop853":
+        raise NotImplementedError("only method='dop853' is implemented on the GPU")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nx, ny = len(x), len(y)
+    if blocks is None:
+        blocks = [row_block(nx, world, r) for r in range(world)]
+    i0, i1 = blocks[rank]
+    rows = i1 - i0
+    W = 2
+    if world > 1 and min(b - a for a, b in blocks) < W:
+        raise ValueError("every rank needs at least 2 rows for the two-row halo exchange")
+    has_lo, has_hi = int(rank > 0), int(rank < world - 1)
+    integrate, _ = backend if backend is not None else _cuda_backend()
+    ridge_tail = ridge_backend if ridge_backend is not None else _cuda_ridge_backend()
+    device = "cuda" if backend is None else "cpu"
+    slab = torch.empty((W * has_lo + rows + W * has_hi, ny, 2), dtype=torch.float64, device=device)
+    own = slab[W * has_lo:W * has_lo + rows]
+    info = {} if info is None else info
+    integrate(funcptr, t0, T, x[i0:i1], y, params, method, rtol, atol, own, info)
+    if world > 1:
+        exchange_halo_rows(slab, has_lo, has_hi, rank, group, width=W)
+    x_slab = x[i0 - W * has_lo:i1 + W * has_hi]
+    ftle_slab, pts = ridge_tail(slab, T, dx, dy, x_slab, y, sdd_thresh)
+    # FTLE rows of the slab are valid from slab row 1 on (row 0 / m-1 lack a neighbour): the owned
+    # rows are at offset 2*has_lo, except that global rows 0 and nx-1 are border rows (ftle = 0)
+    return own, ftle_slab[W * has_lo:W * has_lo + rows], pts, (i0, i1)
+
+
+def gather_points(pts, group=None, dst=0):
+    """Concatenate per-rank point lists [k_r, 2] in rank order on `dst` (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world == 1:
+        return pts
+    n = torch.tensor([pts.shape[0]], dtype=torch.int64, device=pts.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    kmax = int(max(int(c) for c in counts))
+    pad = torch.zeros((max(kmax, 1), 2), dtype=pts.dtype, device=pts.device)
+    pad[:pts.shape[0]] = pts
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][:int(counts[r])] for r in range(world)], dim=0)
 
 
 def gather_rows(block, nx, group=None, dst=0):

@@ -97,8 +97,8 @@ def lib():
         L.oracle_ftle_from_eig.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p]
         L.oracle_ftle_ridge_pts.restype = C.c_int64
         L.oracle_ftle_ridge_pts.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
-                                            C.c_void_p, C.c_double, C.c_double, C.c_void_p,
-                                            C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_double, C.c_double, C.c_double,
+                                            C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_flowmap_composition.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
@@ -397,18 +397,19 @@ def ftle_from_eig(eigval_max, T):
     return out
 
 
-def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
+def _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, spacing=None):
     f, ev, x, y = _f64(f), _f64(eigvec_max), _f64(x), _f64(y)
+    dx, dy = (x[1] - x[0], y[1] - y[0]) if spacing is None else spacing
     nx, ny = f.shape
     f_min = 0.0 if percentile == 0 else float(np.percentile(f, percentile))
     r_pts, r_vec, sdd = np.zeros((nx * ny, 3)), np.zeros((nx * ny, 2)), np.zeros(nx * ny)
-    lib().oracle_ftle_ridge_pts(_ptr(f), _ptr(ev), nx, ny, _ptr(x), _ptr(y), float(sdd_thresh),
-                                f_min, _ptr(r_pts), _ptr(r_vec), _ptr(sdd))
+    lib().oracle_ftle_ridge_pts(_ptr(f), _ptr(ev), nx, ny, _ptr(x), _ptr(y), float(dx), float(dy),
+                                float(sdd_thresh), f_min, _ptr(r_pts), _ptr(r_vec), _ptr(sdd))
     return r_pts, r_vec, sdd, min(x[1] - x[0], y[1] - y[0])
 
 
-def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0):
-    r_pts, _, sdd, _ = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)
+def ftle_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, spacing=None):
+    r_pts, _, sdd, _ = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile, spacing)
     return r_pts[sdd < -sdd_thresh][:, :2]  # sdd is c2 (< -sdd_thresh <= 0) at ridge points, else 0
 
 

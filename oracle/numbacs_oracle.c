@@ -852,10 +852,12 @@ void oracle_ftle_from_eig(const double *eigval_max, int64_t n, double T, double 
  * point), r_vec[nx*ny, 2], sdd[nx*ny].  f_min is 0 or np.percentile(f, percentile), computed by
  * the caller.  Returns the number of ridge points. */
 int64_t oracle_ftle_ridge_pts(const double *f, const double *evec, int64_t nx, int64_t ny,
-                              const double *x, const double *y, double sdd_thresh, double f_min,
-                              double *r_pts, double *r_vec, double *sdd)
+                              const double *x, const double *y, double dx, double dy,
+                              double sdd_thresh, double f_min, double *r_pts, double *r_vec,
+                              double *sdd)
 {
-    double dx = x[1] - x[0], dy = y[1] - y[0];
+    /* dx = x[1] - x[0], dy = y[1] - y[0] (ridges.py:39-40), passed by the caller so that a row
+     * slab of a larger grid can use the spacing of the full grid */
     for (int64_t q = 0; q < nx * ny; ++q) {
         r_pts[3 * q] = r_pts[3 * q + 1] = r_pts[3 * q + 2] = -1.0;
         r_vec[2 * q] = r_vec[2 * q + 1] = 0.0;

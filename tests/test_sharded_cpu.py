@@ -63,6 +63,57 @@ def _worker(rank, world, port, nx, ny, out_path):
     dist.destroy_process_group()
 
 
+def _oracle_ridge_backend():
+    import torch
+    import oracle as O
+
+    def ridge_tail(slab, T, dx, dy, x_slab, y, sdd_thresh):
+        vals, vecs = O.C_eig_2D(slab.numpy(), dx, dy)
+        ftle = O.ftle_from_eig(vals[:, :, 1], T)
+        pts = O.ftle_ridge_pts(ftle, vecs[:, :, :, 1], np.asarray(x_slab), np.asarray(y), sdd_thresh, 0,
+                               spacing=(dx, dy))
+        return torch.from_numpy(ftle), torch.from_numpy(np.ascontiguousarray(pts))
+
+    return ridge_tail
+
+
+def _ridge_worker(rank, world, port, nx, ny, out_path):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from numbacs_b200.sharded import flowmap_ridges_sharded, gather_points, gather_rows
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    params = np.array([1.0, 0.1, 0.25, 0.0, 0.2 * np.pi, 0.0])
+    fm, ft, pts, (i0, i1) = flowmap_ridges_sharded(
+        0, 0.0, 8.0, x, y, params, x[1] - x[0], y[1] - y[0], sdd_thresh=1.0,
+        backend=_oracle_backend(), ridge_backend=_oracle_ridge_backend())
+    ft_all = gather_rows(ft.contiguous(), nx)
+    pts_all = gather_points(pts)
+    if rank == 0:
+        np.savez(out_path, ft=ft_all.numpy(), pts=pts_all.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,nx", [(2, 40), (3, 41)])
+def test_sharded_ridge_tail_equals_single_process(tmp_path, oracle, world, nx):
+    """Two-row halo: C_eig_2D -> ftle_from_eig -> ridge points per row block == single process."""
+    import torch.multiprocessing as mp
+    ny = 23
+    out = str(tmp_path / "ridges.npz")
+    mp.spawn(_ridge_worker, args=(world, _free_port(), nx, ny, out), nprocs=world, join=True)
+    got = np.load(out)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    f, p, _ = oracle.get_predefined_flow("double_gyre")
+    fm = oracle.flowmap_grid_2D(f, 0.0, 8.0, x, y, p)
+    vals, vecs = oracle.C_eig_2D(fm, x[1] - x[0], y[1] - y[0])
+    ft = oracle.ftle_from_eig(vals[:, :, 1], 8.0)
+    pts = oracle.ftle_ridge_pts(ft, vecs[:, :, :, 1], x, y, 1.0, 0)
+    assert len(pts) > 5
+    assert np.array_equal(got["ft"], ft)
+    assert np.array_equal(got["pts"], pts)
+
+
 @pytest.mark.parametrize("world,nx", [(2, 24), (3, 23), (4, 3)])
 def test_sharded_equals_single_process(tmp_path, oracle, world, nx):
     import torch.multiprocessing as mp
