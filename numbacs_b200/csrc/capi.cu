@@ -484,12 +484,17 @@ int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, 
         }
         In<uint8_t> dmask(mask, np, s);  // staged once, used by both kernels
         const bool host_ftle = !is_device_ptr(ftle_out);
-        constexpr long long kChunkRows = 1024;
-        if ((host_ftle || fm_host_copy) && nx >= 2 * kChunkRows && np >= (size_t(1) << 22)) {
+        // ~16 chunks per call, 128..1024 rows each (a multiple of 8)
+        long long chunk_rows = ((nx + 15) / 16 + 7) / 8 * 8;
+        chunk_rows = chunk_rows < 128 ? 128 : (chunk_rows > 1024 ? 1024 : chunk_rows);
+        if ((host_ftle || fm_host_copy) && nx >= 2 * chunk_rows && np >= (size_t(1) << 22)) {
             // Host outputs on a large grid: pipeline.  Rows are integrated in chunks; as soon as a
             // chunk's successor has been integrated its FTLE rows are complete and go out over
-            // PCIe on a second stream while the next chunk is being integrated (the integration
-            // is compute-bound, the download is free).
+            // PCIe while the next chunks are being integrated (the integration is compute-bound,
+            // the download is free).  Consecutive chunks alternate between two streams so that the
+            // tail of one chunk's kernel (SMs idling while the last blocks finish) is filled by the
+            // head of the next; the FTLE kernels and the copies run on high-priority streams so
+            // that they are not queued behind whole integration chunks.
             In<double> dxs(x, nx, s), dys(y, ny, s);
             Out<int32_t> dstatus(status, np, s);
             Out<int64_t> dstats(stats, 3, s, /*upload_first=*/true);
@@ -499,26 +504,47 @@ int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, 
                 ftle_tmp = Scratch((size_t)rows_out * ny * sizeof(double), s);
                 ftle_dev = static_cast<double *>(ftle_tmp.ptr);
             }
-            cudaStream_t s2 = nullptr;
-            B2_CHECK_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+            int prio_lo = 0, prio_hi = 0;
+            B2_CHECK_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            cudaStream_t sI[2] = {nullptr, nullptr}, sF = nullptr, s2 = nullptr;
             std::vector<cudaEvent_t> events;
+            auto new_event = [&](cudaStream_t on) {
+                cudaEvent_t ev;
+                B2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                events.push_back(ev);
+                B2_CHECK_CUDA(cudaEventRecord(ev, on));
+                return ev;
+            };
+            auto cleanup = [&] {
+                for (cudaStream_t st : {sI[0], sI[1], sF, s2})
+                    if (st) cudaStreamSynchronize(st);
+                for (cudaEvent_t ev : events) cudaEventDestroy(ev);
+                for (cudaStream_t st : {sI[0], sI[1], sF, s2})
+                    if (st) cudaStreamDestroy(st);
+            };
             long long ftle_done = halo_lo, fm_done = 0;
             try {
-                for (long long c0 = 0; c0 < nx; c0 += kChunkRows) {
-                    const long long c1 = (c0 + kChunkRows < nx) ? c0 + kChunkRows : nx;
+                B2_CHECK_CUDA(cudaStreamCreateWithPriority(&sI[0], cudaStreamNonBlocking, prio_lo));
+                B2_CHECK_CUDA(cudaStreamCreateWithPriority(&sI[1], cudaStreamNonBlocking, prio_lo));
+                B2_CHECK_CUDA(cudaStreamCreateWithPriority(&sF, cudaStreamNonBlocking, prio_hi));
+                B2_CHECK_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio_hi));
+                const cudaEvent_t ev_start = new_event(s);  // uploads / allocations on the caller's stream
+                for (cudaStream_t st : {sI[0], sI[1], sF, s2}) B2_CHECK_CUDA(cudaStreamWaitEvent(st, ev_start, 0));
+                int k = 0;
+                for (long long c0 = 0; c0 < nx; c0 += chunk_rows, ++k) {
+                    const long long c1 = (c0 + chunk_rows < nx) ? c0 + chunk_rows : nx;
+                    cudaStream_t si = sI[k & 1];
                     run_flowmap(flow, t0, T, true, dxs.dev + c0, c1 - c0, dys.dev, ny, nullptr, 0, 2, params,
                                 nparams, method, rtol, atol, dmask.dev ? dmask.dev + c0 * ny : nullptr, 0,
                                 fm_dev + c0 * ny * 2, nullptr, dstatus.dev ? dstatus.dev + c0 * ny : nullptr,
-                                nullptr, dstats.dev, s);
+                                nullptr, dstats.dev, si);
+                    // sF sees the chunks in order: it waited for chunk k-1 in the previous iteration
+                    B2_CHECK_CUDA(cudaStreamWaitEvent(sF, new_event(si), 0));
                     const long long hi = (c1 == nx) ? (long long)nx - halo_hi : c1 - 1;  // stencil complete below hi
                     if (hi > ftle_done)
                         launch_ftle(fm_dev, nx, ny, T, dx, dy, dmask.dev, ftle_dev + (ftle_done - halo_lo) * ny,
-                                    ftle_done, hi, halo_lo == 0, halo_hi == 0, s);
-                    cudaEvent_t ev;
-                    B2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                    events.push_back(ev);
-                    B2_CHECK_CUDA(cudaEventRecord(ev, s));
-                    B2_CHECK_CUDA(cudaStreamWaitEvent(s2, ev, 0));
+                                    ftle_done, hi, halo_lo == 0, halo_hi == 0, sF);
+                    B2_CHECK_CUDA(cudaStreamWaitEvent(s2, new_event(sF), 0));
                     if (host_ftle && hi > ftle_done)
                         B2_CHECK_CUDA(cudaMemcpyAsync(ftle_out + (ftle_done - halo_lo) * ny,
                                                       ftle_dev + (ftle_done - halo_lo) * ny,
@@ -531,18 +557,16 @@ int b200cs_flowmap_ftle_grid_2d(int flow, double t0, double T, const double *x, 
                     if (hi > ftle_done) ftle_done = hi;
                     fm_done = c1;
                 }
+                // the caller's stream continues after everything issued above
+                B2_CHECK_CUDA(cudaStreamWaitEvent(s, new_event(s2), 0));
                 dstatus.download();
                 dstats.download();
-                B2_CHECK_CUDA(cudaStreamSynchronize(s2));
                 B2_CHECK_CUDA(cudaStreamSynchronize(s));
             } catch (...) {
-                cudaStreamSynchronize(s2);
-                for (cudaEvent_t ev : events) cudaEventDestroy(ev);
-                cudaStreamDestroy(s2);
+                cleanup();
                 throw;
             }
-            for (cudaEvent_t ev : events) cudaEventDestroy(ev);
-            cudaStreamDestroy(s2);
+            cleanup();
             return;
         }
         run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
