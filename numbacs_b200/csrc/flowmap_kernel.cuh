@@ -29,9 +29,12 @@ struct KernelShape {
     static constexpr int kMinBlocks = 1;
     static constexpr bool kLockstep = false;
 };
+#ifndef B200CS_DG_THREADS
+#define B200CS_DG_THREADS 640
+#endif
 template <>
 struct KernelShape<DoubleGyre, false> {
-    static constexpr int kThreads = 640;
+    static constexpr int kThreads = B200CS_DG_THREADS;
     static constexpr int kMinBlocks = 1;
     static constexpr bool kLockstep = true;
 };
