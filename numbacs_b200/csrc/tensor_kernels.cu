@@ -283,7 +283,8 @@ ridge_detect_kernel(const __grid_constant__ RidgeArgs R, double *__restrict__ r_
     if (block_counts && threadIdx.x == 0) block_counts[blockIdx.x] = cnt;
 }
 
-// pass 2: exclusive scan of the block counts (one block; nblocks is at most a few million)
+// pass 2: exclusive scan of the block counts (one block; nblocks is at most a few million, every
+// thread takes four consecutive counts per round so a million counts are 256 rounds)
 __global__ void __launch_bounds__(1024)
 scan_counts_kernel(const int *__restrict__ counts, long long nblocks, long long *__restrict__ offsets,
                    long long *__restrict__ total) {
@@ -292,9 +293,12 @@ scan_counts_kernel(const int *__restrict__ counts, long long nblocks, long long 
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (long long base = 0; base < nblocks; base += 1024) {
-        const long long idx = base + threadIdx.x;
-        const long long v = (idx < nblocks) ? counts[idx] : 0;
+    for (long long base = 0; base < nblocks; base += 4096) {
+        const long long idx = base + 4LL * threadIdx.x;
+        int c[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) c[k] = (idx + k < nblocks) ? counts[idx + k] : 0;
+        const long long v = (long long)c[0] + c[1] + c[2] + c[3];
         long long inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -314,8 +318,12 @@ scan_counts_kernel(const int *__restrict__ counts, long long nblocks, long long 
         }
         __syncthreads();
         const long long carry = carry_s;
-        const long long warp_off = (wid > 0) ? warp_sums[wid - 1] : 0;
-        if (idx < nblocks) offsets[idx] = carry + warp_off + inc - v;
+        long long run = carry + ((wid > 0) ? warp_sums[wid - 1] : 0) + inc - v;  // exclusive prefix of c[0]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (idx + k < nblocks) offsets[idx + k] = run;
+            run += c[k];
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_sums[31];
         __syncthreads();
