@@ -183,7 +183,14 @@ def run_b200(args):
     if _lib.device_count() < 1:
         raise RuntimeError("no CUDA device: bench.py --impl b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    saved_stdout = None
     if world > 1:
+        # NCCL prints its version banner to stdout (fd 1) when NCCL_DEBUG=VERSION/INFO is set in the
+        # environment; the contract is ONE JSON line on stdout, so fd 1 points at stderr until the
+        # line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = args.n
     K, W = args.steps, args.warmup
@@ -408,6 +415,9 @@ def run_b200(args):
             "ftle_checksum": checksum,
             "fp64_peak_tflops_measured": fp64_peak,
         }
+        sys.stdout.flush()
+        if saved_stdout is not None:
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
