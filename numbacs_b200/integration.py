@@ -21,6 +21,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D",
+           "flowmap_grid_ND", "flowmap_n_grid_ND",
            "flowmap_composition", "flowmap_composition_initial", "flowmap_composition_step"]
 
 
@@ -131,6 +132,33 @@ def flowmap_aux_grid_2D(funcptr, t0, T, x, y, params, h=1e-5, eig_main=True, com
         float(atol), ma.ptr, out.ptr, status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
     _fill_info(info, status, steps, stats)
     return out.obj
+
+
+def _flat_points(IC_flat, ndims):
+    """IC_flat (npts * ndims,) -> (npts, ndims) view: particle k is IC_flat[k*ndims:(k+1)*ndims]
+    (integration.py:224, 586), i.e. exactly the row-major point list the pts kernels take."""
+    nd = int(ndims)
+    if _lib._is_torch(IC_flat):
+        flat = IC_flat.reshape(-1)
+    else:
+        flat = np.asarray(IC_flat, dtype=np.float64).reshape(-1)
+    npts = int(flat.shape[0] // nd)
+    return flat[:npts * nd].reshape(npts, nd)
+
+
+def flowmap_grid_ND(funcptr, t0, T, IC_flat, ndims, params, method="dop853", rtol=1e-6, atol=1e-8,
+                    *, device_out=False, info=None):
+    """Final positions for a flattened list of ndims-dimensional initial conditions -> (npts, ndims)
+    (integration.py:185-246; e.g. a 3-D grid for the abc flow)."""
+    return _pts(funcptr, t0, T, _flat_points(IC_flat, ndims), params, 0, method, rtol, atol, None,
+                device_out, info)[0]
+
+
+def flowmap_n_grid_ND(funcptr, t0, T, IC_flat, ndims, params, n=50, method="dop853", rtol=1e-6,
+                      atol=1e-8, *, device_out=False, info=None):
+    """Positions at n equally spaced times -> ((npts, n, ndims), t_eval[n]) (integration.py:536-606)."""
+    return _pts(funcptr, t0, T, _flat_points(IC_flat, ndims), params, n, method, rtol, atol, None,
+                device_out, info)
 
 
 # ---- flow-map composition (integration.py:609-737): FTLE time series from short flow maps ----------

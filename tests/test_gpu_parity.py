@@ -630,3 +630,25 @@ def test_linear_flow(nb, lib, oracle, golden):
     g = _gpu_rhs(lib, fs, -tq, q, np.array([-1.0]))
     o = np.array([fso.rhs(-tq[i], q[i], np.array([-1.0])) for i in range(len(tq))])
     assert np.abs(g - o).max() <= 1e-13 * np.abs(o).max()
+
+
+def test_flowmap_grid_ND(nb, oracle):
+    """flowmap_grid_ND / flowmap_n_grid_ND (integration.py:185-246, 536-606): flattened 3-D initial
+    conditions through the abc flow == the point-list form, and within tolerance of the oracle."""
+    g = np.linspace(0.3, 5.9, 7)
+    X, Y, Z = np.meshgrid(g, g, g, indexing="ij")
+    pts = np.column_stack((X.ravel(), Y.ravel(), Z.ravel()))
+    f, p, _ = nb.flows.get_predefined_flow("abc")
+    fo, po, _ = oracle.get_predefined_flow("abc")
+    fm = nb.integration.flowmap_grid_ND(f, 0.0, 2.0, pts.ravel(), 3, p)
+    assert fm.shape == (343, 3)
+    assert np.array_equal(fm, nb.integration.flowmap(f, 0.0, 2.0, pts, p))
+    assert np.abs(fm - oracle.flowmap(fo, 0.0, 2.0, pts, po)).max() <= 1e-8 * 2 * np.pi
+    fmn, ts = nb.integration.flowmap_n_grid_ND(f, 0.0, 2.0, pts.ravel(), 3, p, n=5)
+    assert fmn.shape == (343, 5, 3) and np.allclose(ts, np.linspace(0, 2, 5))
+    assert np.array_equal(fmn[:, -1], fm) and np.array_equal(fmn[:, 0], pts)
+    # 2-D flows work the same way
+    f2, p2, _ = nb.flows.get_predefined_flow("double_gyre")
+    q = np.column_stack((np.linspace(0.1, 1.9, 50), np.linspace(0.1, 0.9, 50)))
+    assert np.array_equal(nb.integration.flowmap_grid_ND(f2, 0.0, 5.0, q.ravel(), 2, p2),
+                          nb.integration.flowmap(f2, 0.0, 5.0, q, p2))
