@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Throughput + parity spot checks for BASELINE configs 1-4 (config 5 is bench.py).
 
-    python tools/bench_configs.py > gpurun_out/configs.json
+    python tests/perf/bench_configs.py > gpurun_out/configs.json
 
 Each config runs through the public Python API with device-resident tensors, is timed with CUDA
 events (best of 3 after a warm-up), and a random subsample of its particles is re-integrated by the
@@ -12,7 +12,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 

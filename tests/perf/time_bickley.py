@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Config 2 (bickley_jet 2001 x 601, T = +6): device-timed flow map + FTLE and the test-suite's
-parity figures against the oracle on a 4000-particle sample.   [B200CS_LIB=...] python tools/time_bickley.py"""
+parity figures against the oracle on a 4000-particle sample.   [B200CS_LIB=...] python tests/perf/time_bickley.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import oracle as O
 from numbacs_b200 import _lib

@@ -1,13 +1,13 @@
 #!/usr/bin/env python
 """Time the double-gyre flow map + FTLE (device-resident, CUDA events) and check parity on config 1.
 
-    [B200CS_LIB=...] python tools/time_dg.py [n=8192] [reps=3]
+    [B200CS_LIB=...] python tests/perf/time_dg.py [n=8192] [reps=3]
 Prints M points/s (best and median of reps), and for the 401x201 README case the number of
 particles whose step sequence differs from the CPU oracle's and max|dx| over the rest."""
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 
