@@ -18,7 +18,7 @@ from .flows import ScalarField
 from .integration import _info_bufs, _fill_info, _method
 
 __all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D",
-           "lavd_flowmap_grid_2D", "C_tensor_2D", "C_eig_aux_2D", "C_eig_2D", "ftle_from_eig"]
+           "lavd_flowmap_grid_2D", "lavd_vort_sums", "C_tensor_2D", "C_eig_aux_2D", "C_eig_2D", "ftle_from_eig"]
 
 
 def ftle_grid_2D(flowmap, T, dx, dy, mask=None, *, device_out=False):
@@ -125,6 +125,20 @@ def lavd_flowmap_grid_2D(funcptr, t0, T, x, y, params, vort_interp, n=50, method
     if info is not None:
         info["status"], info["stats"] = status.obj, stats.obj
     return (lavd.obj, tspan, fm.obj) if return_flowmap else (lavd.obj, tspan)
+
+
+def lavd_vort_sums(vort_interp, tspan, xrav, yrav, *, device_out=False):
+    """sums[k] = sum_q vort(tspan[k], xrav[q], yrav[q]): the un-normalised spatial mean of
+    lavd_grid_2D (diagnostics.py:324-331).  The multi-GPU driver all-reduces these n doubles."""
+    if not isinstance(vort_interp, ScalarField):
+        raise NotImplementedError("vort_interp must come from numbacs_b200.flows.get_callable_scalar(_linear)")
+    ts, xr, yr = _lib.arg_in(tspan), _lib.arg_in(xrav), _lib.arg_in(yrav)
+    n, nrav = int(ts.obj.shape[0]), int(xr.obj.shape[0])
+    dev = bool(device_out or xr.on_device)
+    out = _lib.alloc_out((n,), np.float64, dev)
+    _lib.check(_lib.load().b200cs_lavd_vort_sums(vort_interp.handle, ts.ptr, n, xr.ptr, yr.ptr, nrav,
+                                                 out.ptr, _lib.current_stream(dev)))
+    return out.obj
 
 
 def _aux_in(flowmap_aux):

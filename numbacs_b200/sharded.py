@@ -7,7 +7,8 @@ communication at all.  The FTLE stencil needs the flow map at rows i-1 / i+1
 (/root/reference/src/numbacs/utils.py:41-44): each rank sends its first / last flow-map row
 (ny x 2 float64 = 262 KB at ny = 16384) to its lower / upper neighbour -- one point-to-point
 exchange, the only data-path collective -- and an optional gather assembles the result on rank 0.
-The ridge tail of config 5 (Cauchy-Green eigen-pairs -> FTLE -> ridge points) widens the halo to
+LAVD needs one all-reduce of n doubles (the spatial-mean vorticity per output time,
+lavd_flowmap_sharded).  The ridge tail of config 5 (Cauchy-Green eigen-pairs -> FTLE -> ridge points) widens the halo to
 two rows and is otherwise local (flowmap_ridges_sharded).
 
 Spline coefficient arrays are replicated: every rank creates its own flow handle.
@@ -15,7 +16,8 @@ Spline coefficient arrays are replicated: every rank creates its own flow handle
 import numpy as np
 
 __all__ = ["row_block", "balanced_row_blocks", "estimate_row_cost", "exchange_halo_rows",
-           "flowmap_ftle_sharded", "flowmap_ridges_sharded", "gather_rows", "gather_points"]
+           "flowmap_ftle_sharded", "flowmap_ridges_sharded", "lavd_flowmap_sharded", "gather_rows",
+           "gather_points"]
 
 
 def row_block(nx, world_size, rank):
@@ -195,6 +197,69 @@ def flowmap_ridges_sharded(funcptr, t0, T, x, y, params, dx, dy, sdd_thresh=0.0,
     # FTLE rows of the slab are valid from slab row 1 on (row 0 / m-1 lack a neighbour): the owned
     # rows are at offset 2*has_lo, except that global rows 0 and nx-1 are border rows (ftle = 0)
     return own, ftle_slab[W * has_lo:W * has_lo + rows], pts, (i0, i1)
+
+
+def output_times(t0, T, n, p0):
+    """tspan[k] = p0 * (p0 * linspace(t0, t0 + T, n))[k] exactly as flowmap_n_grid_2D returns it
+    (integration.py:514, 533; numba linspace = start + k*step, last point forced to stop)."""
+    step = ((t0 + T) - t0) / (n - 1)
+    te = [p0 * (t0 + k * step) for k in range(n - 1)] + [p0 * (t0 + T)]
+    return np.array([p0 * v for v in te], dtype=np.float64)
+
+
+def _cuda_lavd_backend():
+    from .diagnostics import lavd_flowmap_grid_2D, lavd_vort_sums
+
+    def vort_sums(vort_interp, tspan, x_rows, y):
+        import torch
+        X, Y = torch.meshgrid(x_rows, y, indexing="ij")
+        return lavd_vort_sums(vort_interp, tspan, X.reshape(-1), Y.reshape(-1), device_out=True)
+
+    def lavd(funcptr, t0, T, x_rows, y, params, vort_interp, n, rtol, atol, px, py, vort_avg):
+        out, _ = lavd_flowmap_grid_2D(funcptr, t0, T, x_rows, y, params, vort_interp, n=n, rtol=rtol,
+                                      atol=atol, period_x=px, period_y=py, vort_avg=vort_avg,
+                                      device_out=True)
+        return out
+
+    return vort_sums, lavd
+
+
+def lavd_flowmap_sharded(funcptr, t0, T, x, y, params, vort_interp, n=50, method="dop853", rtol=1e-6,
+                         atol=1e-8, period_x=0.0, period_y=0.0, *, group=None, backend=None,
+                         blocks=None):
+    """LAVD (flowmap_n_grid_2D + lavd_grid_2D, fused) on row blocks.  The only exchange is the
+    spatial-mean vorticity per output time (diagnostics.py:324-331): every rank sums the vorticity
+    over ITS rows of the initial grid, an all-reduce(sum) of n doubles makes the global means, and
+    the fused trajectory kernel then runs without any further communication.
+
+    Returns (lavd_block [rows, ny], tspan [n], (i0, i1)).  x, y: torch tensors (CUDA for the
+    product path)."""
+    import torch
+    import torch.distributed as dist
+    if method.lower() != "dop853":
+        raise NotImplementedError("only method='dop853' is implemented on the GPU")
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    nx, ny = len(x), len(y)
+    if blocks is None:
+        blocks = [row_block(nx, world, r) for r in range(world)]
+    i0, i1 = blocks[rank]
+    vort_sums, lavd = backend if backend is not None else _cuda_lavd_backend()
+    p0 = float(params[0])
+    tspan = output_times(float(t0), float(T), int(n), p0)
+    x_rows = x[i0:i1]
+    if i1 > i0:
+        sums = vort_sums(vort_interp, tspan, x_rows, y)
+    else:
+        sums = torch.zeros(n, dtype=torch.float64, device=x.device)
+    if world > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)   # n doubles: the only collective
+    vort_avg = sums / float(nx * ny)
+    if i1 > i0:
+        out = lavd(funcptr, t0, T, x_rows, y, params, vort_interp, n, rtol, atol, period_x, period_y, vort_avg)
+    else:
+        out = torch.empty((0, ny), dtype=torch.float64, device=x.device)
+    return out, tspan, (i0, i1)
 
 
 def gather_points(pts, group=None, dst=0):

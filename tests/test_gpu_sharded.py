@@ -108,3 +108,65 @@ def test_multi_gpu_ridge_tail_matches_single_gpu(tmp_path, lib):
     assert len(pts) > 100
     assert np.array_equal(got["ft"], ft)
     assert np.array_equal(got["pts"], pts)
+
+
+def _lavd_fields():
+    t, xs, ys = np.linspace(0, 10, 17), np.linspace(0, 2, 33), np.linspace(0, 1, 25)
+    T, X, Y = np.meshgrid(t, xs, ys, indexing="ij")
+    a = 0.25 * np.sin(0.2 * np.pi * T)
+    b = 1 - 2 * a
+    f = a * X ** 2 + b * X
+    U = -np.pi * 0.1 * np.sin(np.pi * f) * np.cos(np.pi * Y)
+    V = np.pi * 0.1 * np.cos(np.pi * f) * np.sin(np.pi * Y) * (2 * a * X + b)
+    vort = np.sin(3 * X + 0.3 * T) * np.cos(2 * Y)
+    return t, xs, ys, U, V, vort
+
+
+def _lavd_worker(rank, world, port, nx, ny, n, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from numbacs_b200 import flows
+    from numbacs_b200.sharded import gather_rows, lavd_flowmap_sharded
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    t, xs, ys, U, V, vort = _lavd_fields()
+    grid, Cu, Cv = flows.get_interp_arrays_2D(t, xs, ys, U, V)
+    f = flows.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")          # coefficients replicated per rank
+    gw, Cw = flows.get_interp_arrays_scalar(t, xs, ys, vort)
+    w = flows.get_callable_scalar(gw, Cw, extrap_mode="linear")
+    x = torch.linspace(0.1, 1.9, nx, dtype=torch.float64, device="cuda")
+    y = torch.linspace(0.1, 0.9, ny, dtype=torch.float64, device="cuda")
+    lavd, ts, _ = lavd_flowmap_sharded(f, 1.0, 6.0, x, y, np.array([1.0]), w, n=n)
+    full = gather_rows(lavd.contiguous(), nx)
+    if rank == 0:
+        np.savez(out_path, lavd=full.cpu().numpy(), ts=ts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_multi_gpu_lavd_matches_single_gpu(tmp_path, lib):
+    """Row-sharded fused LAVD with the NCCL all-reduce of the mean vorticity == single-GPU call."""
+    torch = pytest.importorskip("torch")
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    from numbacs_b200 import flows
+    from numbacs_b200.diagnostics import lavd_flowmap_grid_2D
+    world = min(torch.cuda.device_count(), 4)
+    nx, ny, n = 203, 97, 41
+    out = str(tmp_path / "lavd.npz")
+    mp.spawn(_lavd_worker, args=(world, _free_port(), nx, ny, n, out), nprocs=world, join=True)
+    got = np.load(out)
+    t, xs, ys, U, V, vort = _lavd_fields()
+    grid, Cu, Cv = flows.get_interp_arrays_2D(t, xs, ys, U, V)
+    f = flows.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")
+    gw, Cw = flows.get_interp_arrays_scalar(t, xs, ys, vort)
+    w = flows.get_callable_scalar(gw, Cw, extrap_mode="linear")
+    x = torch.linspace(0.1, 1.9, nx, dtype=torch.float64).numpy()
+    y = torch.linspace(0.1, 0.9, ny, dtype=torch.float64).numpy()
+    ref, ts = lavd_flowmap_grid_2D(f, 1.0, 6.0, x, y, np.array([1.0]), w, n=n)
+    assert np.array_equal(got["ts"], ts)
+    # the mean is summed in a different order (per-rank partial sums): rounding-level agreement
+    assert np.abs(got["lavd"] - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())

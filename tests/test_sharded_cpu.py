@@ -95,6 +95,76 @@ def _ridge_worker(rank, world, port, nx, ny, out_path):
     dist.destroy_process_group()
 
 
+def _lavd_setup():
+    import oracle as O
+    t, xs, ys = np.linspace(0, 10, 9), np.linspace(0, 2, 17), np.linspace(0, 1, 13)
+    T, X, Y = np.meshgrid(t, xs, ys, indexing="ij")
+    vort = np.sin(3 * X + 0.3 * T) * np.cos(2 * Y)
+    grid = ((t[0], t[-1], len(t)), (xs[0], xs[-1], len(xs)), (ys[0], ys[-1], len(ys)))
+    w = O.get_callable_scalar_linear(grid, vort, extrap_mode="constant")
+    flow, params, _ = O.get_predefined_flow("double_gyre")
+    return O, flow, params, w
+
+
+def _oracle_lavd_backend():
+    import torch
+    O, flow, _, w = _lavd_setup()
+
+    def vort_sums(vort_interp, tspan, x_rows, y):
+        X, Y = np.meshgrid(np.asarray(x_rows), np.asarray(y), indexing="ij")
+        out = [w(np.column_stack((np.full(X.size, tk), X.ravel(), Y.ravel()))).sum() for tk in tspan]
+        return torch.tensor(out, dtype=torch.float64)
+
+    def lavd(funcptr, t0, T, x_rows, y, params, vort_interp, n, rtol, atol, px, py, vort_avg):
+        fmn, ts = O.flowmap_n_grid_2D(flow, t0, T, np.asarray(x_rows), np.asarray(y), np.asarray(params), n=n,
+                                      rtol=rtol, atol=atol)
+        va = vort_avg.numpy()
+        out = np.zeros(fmn.shape[:2])
+        for i in range(fmn.shape[0]):
+            for j in range(fmn.shape[1]):
+                pts = np.column_stack((ts, fmn[i, j, :, 0], fmn[i, j, :, 1]))
+                out[i, j] = O.composite_simpsons(np.abs(w(pts) - va), abs(ts[1] - ts[0]))
+        return torch.from_numpy(out)
+
+    return vort_sums, lavd
+
+
+def _lavd_worker(rank, world, port, nx, ny, n, out_path):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from numbacs_b200.sharded import gather_rows, lavd_flowmap_sharded
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    x, y = torch.linspace(0.1, 1.9, nx, dtype=torch.float64), torch.linspace(0.1, 0.9, ny, dtype=torch.float64)
+    params = np.array([1.0, 0.1, 0.25, 0.0, 0.2 * np.pi, 0.0])
+    lavd, ts, _ = lavd_flowmap_sharded(0, 1.0, 6.0, x, y, params, None, n=n, backend=_oracle_lavd_backend())
+    full = gather_rows(lavd.contiguous(), nx)
+    if rank == 0:
+        np.savez(out_path, lavd=full.numpy(), ts=ts)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lavd_equals_single_process(tmp_path, oracle, world):
+    """Row-sharded LAVD with the all-reduced spatial-mean vorticity == oracle.lavd_grid_2D on the
+    whole grid (the mean is summed in a different order: agreement to rounding, not bits)."""
+    import torch
+    import torch.multiprocessing as mp
+    nx, ny, n = 11, 7, 8
+    out = str(tmp_path / "lavd.npz")
+    mp.spawn(_lavd_worker, args=(world, _free_port(), nx, ny, n, out), nprocs=world, join=True)
+    got = np.load(out)
+    O, flow, params, w = _lavd_setup()
+    x = torch.linspace(0.1, 1.9, nx, dtype=torch.float64).numpy()
+    y = torch.linspace(0.1, 0.9, ny, dtype=torch.float64).numpy()
+    fmn, ts = O.flowmap_n_grid_2D(flow, 1.0, 6.0, x, y, params, n=n)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    ref = O.lavd_grid_2D(fmn, ts, 6.0, w, X.ravel(), Y.ravel())
+    assert np.array_equal(got["ts"], ts)
+    assert np.abs(got["lavd"] - ref).max() <= 1e-13 * max(1.0, np.abs(ref).max())
+
+
 @pytest.mark.parametrize("world,nx", [(2, 40), (3, 41)])
 def test_sharded_ridge_tail_equals_single_process(tmp_path, oracle, world, nx):
     """Two-row halo: C_eig_2D -> ftle_from_eig -> ridge points per row block == single process."""
