@@ -76,6 +76,34 @@ def test_no_cpu_fallback(lib):
         ftle_grid_2D(np.zeros((5, 5, 2)), 8.0, 0.1, 0.1)
 
 
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_for_the_tensor_and_ridge_entries(lib):
+    """Every compute entry added for the section-8(f) rows fails loudly without a GPU."""
+    import numbacs_b200 as nb
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    x, y = np.linspace(0, 2, 7), np.linspace(0, 1, 6)
+    fm, fa = np.zeros((7, 6, 2)), np.zeros((7, 6, 5, 2))
+    grid = ((0.0, 2.0, 7), (0.0, 1.0, 6))
+    calls = [
+        lambda: nb.integration.flowmap_aux_grid_2D(f, 0.0, 1.0, x, y, p),
+        lambda: nb.integration.flowmap_grid_ND(f, 0.0, 1.0, np.zeros(8), 2, p),
+        lambda: nb.integration.flowmap_composition(np.zeros((3, 7, 6, 2)), grid, 3),
+        lambda: nb.integration.flowmap_composition_initial(f, 0.0, 2.0, 1.0, x, y, grid, p),
+        lambda: nb.diagnostics.C_eig_2D(fm, 0.1, 0.1),
+        lambda: nb.diagnostics.C_eig_aux_2D(fa, 0.1, 0.1),
+        lambda: nb.diagnostics.C_tensor_2D(fa, 0.1, 0.1),
+        lambda: nb.diagnostics.ftle_from_eig(np.ones((7, 6)), 2.0),
+        lambda: nb.extraction.ftle_ridge_pts(np.ones((7, 6)), np.ones((7, 6, 2)), x, y),
+        lambda: nb.extraction.ftle_ridges(np.ones((7, 6)), np.ones((7, 6, 2)), x, y),
+        lambda: nb.extraction.percentile_value(np.ones(10), 50),
+        lambda: nb.utils.binary_mask_dilation(np.zeros((7, 6), bool)),
+        lambda: nb.flows.get_flow_linear_2D(((0, 1, 3), (0, 2, 7), (0, 1, 6)), np.zeros((3, 7, 6)), np.zeros((3, 7, 6))),
+    ]
+    for call in calls:
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            call()
+
+
 def test_argument_errors(lib):
     from numbacs_b200.flows import get_predefined_flow
     from numbacs_b200.integration import flowmap_grid_2D

@@ -346,3 +346,64 @@ def test_mask_helpers(nb, golden, oracle):
     ref, _ = nb.diagnostics.C_eig_2D(nb.integration.flowmap_grid_2D(f, 0.0, 5.0, x, y, p), x[1], y[1])
     keep = ~U.binary_mask_dilation(hole)
     assert np.array_equal(vals[keep], ref[keep]) and not vals[~keep].any()
+
+
+# ------------------------------------------------------------------ edge cases
+
+def test_edge_cases_of_the_tensor_and_ridge_entries(nb, oracle):
+    D, E, I = nb.diagnostics, nb.extraction, nb.integration
+    # empty grids
+    vals, vecs = D.C_eig_2D(np.zeros((0, 5, 2)), 0.1, 0.1)
+    assert vals.shape == (0, 5, 2) and vecs.shape == (0, 5, 2, 2)
+    assert D.C_tensor_2D(np.zeros((4, 0, 5, 2)), 0.1, 0.1).shape == (4, 0, 3)
+    assert D.ftle_from_eig(np.zeros((0, 3)), 1.0).shape == (0, 3)
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    assert I.flowmap_aux_grid_2D(f, 0.0, 1.0, np.zeros(0), np.linspace(0, 1, 4), p).shape == (0, 4, 5, 2)
+    # grids smaller than the stencils: everything is border -> zeros / no ridge points
+    rng = np.random.default_rng(4)
+    for shape in ((2, 2), (3, 4), (4, 4)):
+        fm = rng.normal(size=shape + (2,))
+        vals, vecs = D.C_eig_2D(fm, 0.1, 0.2)
+        vo, eo = oracle.C_eig_2D(fm, 0.1, 0.2)
+        assert np.array_equal(vals, vo) and np.array_equal(vecs, eo)
+        fa = rng.normal(size=shape + (5, 2))
+        assert not D.C_tensor_2D(fa, 0.1, 0.2).any()
+        assert not D.C_eig_aux_2D(fa, 0.1, 0.2)[0].any()
+        x, y = np.linspace(0, 1, shape[0]), np.linspace(0, 1, shape[1])
+        r = E.ftle_ridge_pts(rng.random(shape) + 1, rng.normal(size=shape + (2,)), x, y)
+        assert r.shape == (0, 2)
+        assert E.ftle_ridges(rng.random(shape) + 1, rng.normal(size=shape + (2,)), x, y) == []
+    # a field without ridges (monotone ramp), and one where every interior pixel is a ridge point
+    x, y = np.linspace(0, 1, 40), np.linspace(0, 1, 30)
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    ev = np.zeros(X.shape + (2,))
+    ev[..., 0] = 1.0
+    assert E.ftle_ridge_pts(1 + X + Y, ev, x, y).shape == (0, 2)
+    assert E.ftle_ridge_pts(2 - (X - 0.5) ** 2, ev, x, y, percentile=100).shape == (0, 2)   # f > max(f) never
+    bump = 2 - 1e-3 * (X - X.round(1)) ** 2 - (X - 0.5) ** 2        # concave in x everywhere
+    r = E.ftle_ridge_pts(bump, ev, x, y)
+    ro = oracle.ftle_ridge_pts(bump, ev, x, y)
+    assert np.array_equal(r, ro)
+    # more ridge points than the wrapper's first capacity guess (max(4096, pixels / 32)): second call
+    xs, ys = np.linspace(0, 1, 300), np.linspace(0, 1, 300)
+    Xs, Ys = np.meshgrid(xs, ys, indexing="ij")
+    wavy = 2 + np.cos(2 * np.pi * Xs / (3 * (xs[1] - xs[0])))      # a ridge every third column
+    evs = np.zeros(Xs.shape + (2,))
+    evs[..., 0] = 1.0
+    r = E.ftle_ridge_pts(wavy, evs, xs, ys)
+    ro = oracle.ftle_ridge_pts(wavy, evs, xs, ys)
+    assert len(ro) > max(4096, 300 * 300 // 32) and np.array_equal(r, ro)
+    rr = E.ftle_ridges(wavy, evs, xs, ys)
+    rro = oracle.ftle_ridges(wavy, evs, xs, ys)
+    assert [len(a) for a in rr] == [len(a) for a in rro] and np.array_equal(np.concatenate(rr), np.concatenate(rro))
+    # argument errors
+    with pytest.raises(ValueError):
+        D.C_eig_2D(np.zeros((4, 4, 3)), 0.1, 0.1)
+    with pytest.raises(ValueError):
+        D.C_eig_aux_2D(np.zeros((6, 6, 4, 2)), 0.1, 0.1, eig_main=True)
+    with pytest.raises(ValueError):
+        E.ftle_ridge_pts(np.zeros((6, 6)), np.zeros((6, 5, 2)), np.arange(6.0), np.arange(6.0))
+    with pytest.raises(ValueError):
+        I.flowmap_composition(np.zeros((3, 5, 5, 2)), ((0, 1, 5), (0, 1, 6)), 3)
+    with pytest.raises(NotImplementedError):
+        I.flowmap_aux_grid_2D(f, 0.0, 1.0, x, y, p, method="lsoda")
