@@ -215,6 +215,22 @@ B200CS_API int b200cs_flowmap_aux_grid_2d(int flow, double t0, double T, const d
                                double atol, const uint8_t *mask, double *out, int32_t *status,
                                int32_t *steps, int64_t *stats, void *stream);
 
+/* FTLE time series (examples/time_series/plot_dg_time_series.py:100-112 loops flowmap_grid_2D +
+ * ftle_grid_2D over t0; flowmap_composition_initial, integration.py:684-688, loops it over the
+ * nT intermediate maps): all nt frames in ONE launch.  Frame f integrates the (x, y) grid over
+ * [t0s[f], t0s[f] + T]; out is [nt, nx, ny, 2], status [nt, nx, ny], steps [nt, nx, ny, 2]; the
+ * mask [nx, ny] applies to every frame.  Each particle is integrated exactly as by
+ * b200cs_flowmap_grid_2d (bit-identical results). */
+B200CS_API int b200cs_flowmap_grid_2d_series(int flow, const double *t0s, int64_t nt, double T,
+                                  const double *x, int64_t nx, const double *y, int64_t ny,
+                                  const double *params, int nparams, int method, double rtol,
+                                  double atol, const uint8_t *mask, double *out, int32_t *status,
+                                  int32_t *steps, int64_t *stats, void *stream);
+
+/* ftle_grid_2D on every frame of flowmaps [nt, nx, ny, 2] -> ftle [nt, nx, ny], one launch. */
+B200CS_API int b200cs_ftle_series_2d(const double *flowmaps, int64_t nt, int64_t nx, int64_t ny, double T,
+                          double dx, double dy, const uint8_t *mask, double *ftle, void *stream);
+
 /* C_tensor_2D(flowmap_aux, dx, dy, h, mask)    (diagnostics.py:68-112; utils.py:49-84)
  * C[nx, ny, 3] = (C11, C12, C22) on [2, nx-2) x [2, ny-2), 0 elsewhere; dx, dy unused as in the
  * reference. */

@@ -50,6 +50,9 @@ PROTOTYPES = {
     "b200cs_lavd_vort_sums": [_i, _vp, _i64, _vp, _vp, _i64, _vp, _vp],
     "b200cs_flowmap_aux_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _d, _i, _i, _i, _d, _d,
                                    _vp, _vp, _vp, _vp, _vp, _vp],
+    "b200cs_flowmap_grid_2d_series": [_i, _vp, _i64, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp, _vp,
+                                      _vp, _vp, _vp, _vp],
+    "b200cs_ftle_series_2d": [_vp, _i64, _i64, _i64, _d, _d, _d, _vp, _vp, _vp],
     "b200cs_c_tensor_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
     "b200cs_c_eig_2d": [_vp, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp],
     "b200cs_c_eig_aux_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp],

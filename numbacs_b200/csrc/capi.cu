@@ -125,10 +125,12 @@ static void check_device(const FlowSpec &f) {
 }
 
 // common body of flowmap_grid_2d / flowmap_pts
-struct AuxSpec {  // flowmap_aux_grid_2D only
+struct AuxSpec {  // flowmap_aux_grid_2D / time-series calls only
     int n_aux = 0;  // 0: not an aux-grid call
     int edge = 0;
     double h = 0.0;
+    const double *t0s = nullptr;  // non-null: time series of nt frames (t0 is ignored)
+    int64_t nt = 0;
 };
 
 static void run_flowmap(int flow, double t0, double T, bool grid_mode, const double *x, int64_t nx,
@@ -145,7 +147,7 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     B2_REQUIRE(f->kind >= 0, "handle %d is a scalar field, not a flow", flow);
     check_device(*f);
     const long long ncell = grid_mode ? (long long)nx * ny : (long long)npts_in;
-    const long long npts = aux.n_aux ? ncell * aux.n_aux : ncell;
+    const long long npts = aux.n_aux ? ncell * aux.n_aux : (aux.t0s ? ncell * aux.nt : ncell);
     B2_REQUIRE(npts >= 0, "negative particle count");
     if (grid_mode) B2_REQUIRE(f->ndim == 2, "grid entry points need a 2-D flow");
     else B2_REQUIRE(ndim == f->ndim, "pts has %d columns but the flow state is %d-D", ndim, f->ndim);
@@ -168,6 +170,8 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     A.n_aux = aux.n_aux;
     A.aux_edge = aux.edge;
     A.aux_h = aux.h;
+    A.series_T = T;
+    A.frame_pts = ncell;
 
     if (tspan && n >= 2) {
         // returned times are params[0] * t_eval (integration.py:120, 533)
@@ -195,6 +199,8 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
         dpts = In<double>(pts, (size_t)npts * nd, s);
     }
     In<uint8_t> dmask(mask, ncell, s);  // one byte per grid cell / point
+    In<double> dt0s(aux.t0s, aux.t0s ? (size_t)aux.nt : 0, s);
+    A.t0s = dt0s.dev;
     B2_REQUIRE(out, "out must not be null");
     Out<double> dout(out, (size_t)npts * row, s);
     Out<int32_t> dstatus(status, npts, s);
@@ -211,7 +217,7 @@ static void run_flowmap(int flow, double t0, double T, bool grid_mode, const dou
     A.steps = dsteps.dev;
     A.stats = reinterpret_cast<unsigned long long *>(dstats.dev);
 
-    launch_flowmap(*f, A, aux.n_aux ? 2 : (grid_mode ? 1 : 0), s);
+    launch_flowmap(*f, A, aux.n_aux ? 2 : (aux.t0s ? 3 : (grid_mode ? 1 : 0)), s);
 
     dout.download();
     dstatus.download();
@@ -731,6 +737,45 @@ int b200cs_flowmap_aux_grid_2d(int flow, double t0, double T, const double *x, i
         aux.h = h;
         run_flowmap(flow, t0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
                     mask, 0, out, nullptr, status, steps, stats, static_cast<cudaStream_t>(stream), aux);
+    });
+}
+
+int b200cs_flowmap_grid_2d_series(int flow, const double *t0s, int64_t nt, double T, const double *x,
+                                  int64_t nx, const double *y, int64_t ny, const double *params, int nparams,
+                                  int method, double rtol, double atol, const uint8_t *mask, double *out,
+                                  int32_t *status, int32_t *steps, int64_t *stats, void *stream) {
+    return guarded([&] {
+        B2_REQUIRE(nx >= 0 && ny >= 0 && nt >= 0, "negative size");
+        B2_REQUIRE(t0s != nullptr || nt == 0, "t0s is null");
+        if (nt == 0) return;
+        AuxSpec aux;
+        aux.t0s = t0s;
+        aux.nt = nt;
+        run_flowmap(flow, 0.0, T, true, x, nx, y, ny, nullptr, 0, 2, params, nparams, method, rtol, atol,
+                    mask, 0, out, nullptr, status, steps, stats, static_cast<cudaStream_t>(stream), aux);
+    });
+}
+
+int b200cs_ftle_series_2d(const double *flowmaps, int64_t nt, int64_t nx, int64_t ny, double T, double dx,
+                          double dy, const uint8_t *mask, double *ftle, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmaps && ftle, "null argument");
+        B2_REQUIRE(nt >= 0 && nx >= 0 && ny >= 0, "negative size");
+        B2_REQUIRE(T != 0.0 && dx != 0.0 && dy != 0.0, "T, dx and dy must be non-zero");
+        if (nt == 0 || nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmaps, np * 2 * nt, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dout(ftle, np * nt, s);
+        for (int64_t f0 = 0; f0 < nt; f0 += 65535) {
+            const int64_t nf = (nt - f0 < 65535) ? nt - f0 : 65535;
+            launch_ftle(dfm.dev + f0 * np * 2, nx, ny, T, dx, dy, dmask.dev, dout.dev + f0 * np, 0, nx, true,
+                        true, s, nf);
+        }
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
     });
 }
 

@@ -68,7 +68,11 @@ struct RowSink {
 // q = (i*ny + j)*n_aux + k starts at (x[i], y[j]) + aux_grid[k], aux_grid = [(h,0), (-h,0), (0,h),
 // (0,-h), (0,0)]; the n_aux stencil points of a cell are neighbouring lanes (their trajectories
 // and step sequences are practically identical, so they do not diverge).
-constexpr int kModePts = 0, kModeGrid = 1, kModeAux = 2;
+// kModeSeries = the 'ij' grid integrated from nt different initial times in ONE launch (FTLE time
+// series, the intermediate maps of flowmap_composition_initial): particle q belongs to frame
+// q / (nx*ny) and integrates over [t0s[frame], t0s[frame] + T].  A 201 x 101 movie frame is only
+// 20 k particles -- a seventh of one wave of the machine -- so batching the frames is what fills it.
+constexpr int kModePts = 0, kModeGrid = 1, kModeAux = 2, kModeSeries = 3;
 
 template <class Rhs, bool DENSE, int MODE>
 __global__ void __launch_bounds__(KernelShape<Rhs, DENSE>::kThreads, KernelShape<Rhs, DENSE>::kMinBlocks)
@@ -79,7 +83,8 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
     const long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
     const bool in_range = q < A.npts;
     bool active = in_range;
-    if (MODE != kModeAux && active && A.mask != nullptr) active = (A.mask[q] == 0);
+    if (MODE != kModeAux && MODE != kModeSeries && active && A.mask != nullptr) active = (A.mask[q] == 0);
+    double x0 = A.x0, xend = A.xend;   // warp-uniform except in kModeSeries
 
     double y[N];
 #pragma unroll
@@ -101,6 +106,19 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
                 y[1] = A.y[j] + oy;
             }
         }
+    } else if (MODE == kModeSeries) {
+        if (in_range) {
+            const long long frame = q / A.frame_pts, ql = q - frame * A.frame_pts;
+            if (A.mask != nullptr) active = (A.mask[ql] == 0);
+            const double t0 = A.t0s[frame], p0 = A.rhs.p[0];
+            x0 = p0 * t0;                // params[0] * linspace(t0, t0 + T, 2)   (integration.py:164)
+            xend = p0 * (t0 + A.series_T);
+            if (active) {
+                const long long i = ql / A.ny, j = ql - i * A.ny;
+                y[0] = A.x[i];
+                y[1] = A.y[j];
+            }
+        }
     } else if (active) {
         if (MODE == kModeGrid) {
             const long long i = q / A.ny, j = q - i * A.ny;
@@ -118,7 +136,7 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
     double *row = A.out + q * row_len;
 
     const Rhs rhs(A.rhs);
-    const bool integrate = active && (A.xend != A.x0);   // T == 0: the flow map is the identity
+    const bool integrate = active && (xend != x0);   // T == 0: the flow map is the identity
     if (DENSE) {
         RowSink<N> sink{row, A.out_aligned16 != 0};
         if (active) {
@@ -128,10 +146,10 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
         } else if (in_range) {
             for (long long k = 0; k < row_len; ++k) row[k] = 0.0;  // masked: zeros (integration.py:163, 515)
         }
-        status = dop853_integrate<true, kLockstep>(rhs, integrate, y, A.x0, A.xend, A.rtol, A.atol, A.n_out,
+        status = dop853_integrate<true, kLockstep>(rhs, integrate, y, x0, xend, A.rtol, A.atol, A.n_out,
                                                    A.out_p0, A.out_t0, A.out_step, sink, cnt);
     } else {
-        status = dop853_integrate<false, kLockstep>(rhs, integrate, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0,
+        status = dop853_integrate<false, kLockstep>(rhs, integrate, y, x0, xend, A.rtol, A.atol, 0, 0.0, 0.0,
                                                     0.0, NoSink<N>{}, cnt);
     }
     if (active && !integrate) status = B200CS_ST_OK;
@@ -154,7 +172,7 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
     if (A.stats) {
         const int nstep = cnt.accepted + cnt.rejected;
         unsigned long long nfev =
-            active && (A.xend != A.x0) ? 2ull + 11ull * nstep + cnt.accepted + 3ull * cnt.dense : 0ull;
+            integrate ? 2ull + 11ull * nstep + cnt.accepted + 3ull * cnt.dense : 0ull;
         unsigned long long acc = cnt.accepted, rej = cnt.rejected;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -268,12 +286,13 @@ void launch_one(const IntegArgs &A, cudaStream_t s) {
 template <class Rhs>
 void launch_rhs(const IntegArgs &A, int mode, cudaStream_t s) {
     const bool dense = A.n_out >= 2;
-    if (mode == kModeAux) {
+    if (mode == kModeAux || mode == kModeSeries) {
         if constexpr (Rhs::N == 2) {
-            B2_REQUIRE(!dense, "the aux-grid flow map is a final-time quantity");
-            launch_one<Rhs, false, kModeAux>(A, s);
+            B2_REQUIRE(!dense, "the aux-grid / time-series flow maps are final-time quantities");
+            if (mode == kModeAux) launch_one<Rhs, false, kModeAux>(A, s);
+            else launch_one<Rhs, false, kModeSeries>(A, s);
         } else {
-            B2_REQUIRE(false, "the aux grid needs a 2-D flow");
+            B2_REQUIRE(false, "the aux grid and the time series need a 2-D flow");
         }
     } else if (dense) {
         if (mode == kModeGrid) launch_one<Rhs, true, kModeGrid>(A, s);

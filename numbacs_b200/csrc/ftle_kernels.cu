@@ -58,6 +58,9 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
     const long long j = (long long)blockIdx.x * kCols + threadIdx.x;
     const long long i0 = row_lo + (long long)blockIdx.y * kRows;
     if (j >= ny || i0 >= row_hi) return;
+    // blockIdx.z = frame of a time series: frames are consecutive [nx, ny] grids, one mask for all
+    fm += (long long)blockIdx.z * nx * ny;
+    out += (long long)blockIdx.z * (row_hi - row_lo) * ny;
     // everything below the strip origin is 32-bit arithmetic (the launcher checks that a strip of
     // kRows + 3 rows fits in 2^31 elements); only the three base pointers are 64-bit
     const int rows = (int)((row_hi - i0 < kRows) ? (row_hi - i0) : kRows);
@@ -128,12 +131,14 @@ void init_log_table() {
 
 void launch_ftle(const double *fm, long long nx, long long ny, double T, double dx, double dy,
                  const uint8_t *mask, double *out, long long row_lo, long long row_hi,
-                 bool lo_is_border, bool hi_is_border, cudaStream_t s) {
-    if (row_hi <= row_lo || ny <= 0) return;
+                 bool lo_is_border, bool hi_is_border, cudaStream_t s, long long frames) {
+    if (row_hi <= row_lo || ny <= 0 || frames <= 0) return;
+    B2_REQUIRE(frames <= 65535, "too many frames for one FTLE launch (%lld)", frames);
     B2_REQUIRE((reinterpret_cast<uintptr_t>(fm) & 15) == 0, "flow map must be 16-byte aligned");
     init_log_table();
     const double scaling = 1.0 / (2.0 * fabs(T));
-    const dim3 grid((unsigned)((ny + kCols - 1) / kCols), (unsigned)((row_hi - row_lo + kRows - 1) / kRows));
+    const dim3 grid((unsigned)((ny + kCols - 1) / kCols), (unsigned)((row_hi - row_lo + kRows - 1) / kRows),
+                    (unsigned)frames);
     B2_REQUIRE(grid.y <= 65535u, "too many rows for one FTLE launch (%lld)", row_hi - row_lo);
     B2_REQUIRE(ny * (kRows + 4) < 2147483647LL, "ny too large for the FTLE kernel (%lld)", ny);
     ftle_kernel<<<grid, kCols, 0, s>>>(reinterpret_cast<const double2 *>(fm), nx, ny, scaling,

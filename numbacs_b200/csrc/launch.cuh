@@ -24,6 +24,10 @@ struct IntegArgs {
     // auxiliary stencil (flowmap_aux_grid_2D): n_aux = 4 or 5 particles per grid cell, offset h
     int n_aux, aux_edge;
     double aux_h;
+    // time series (kModeSeries): frame f integrates from t0s[f] over series_T; frame_pts = nx*ny
+    const double *t0s;
+    double series_T;
+    long long frame_pts;
     double *out;
     int *status;
     int *steps;
@@ -37,7 +41,8 @@ struct IntegArgs {
     double *lavd;              // [npts]
 };
 
-void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode /*0 pts, 1 grid, 2 aux grid*/, cudaStream_t s);
+void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode /*0 pts, 1 grid, 2 aux grid, 3 time series*/,
+                    cudaStream_t s);
 void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, const double *y,
                      long long npts, double *dy, cudaStream_t s);
 
@@ -45,7 +50,7 @@ void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, con
 // `lo_is_border` / `hi_is_border`: slab row 0 / nx-1 is a true domain border (ftle = 0).
 void launch_ftle(const double *fm, long long nx, long long ny, double T, double dx, double dy,
                  const uint8_t *mask, double *out, long long row_lo, long long row_hi,
-                 bool lo_is_border, bool hi_is_border, cudaStream_t s);
+                 bool lo_is_border, bool hi_is_border, cudaStream_t s, long long frames = 1);
 
 SplineGridDev make_grid_dev(const FlowSpec &f);
 

@@ -17,7 +17,7 @@ from . import _lib
 from .flows import ScalarField
 from .integration import _info_bufs, _fill_info, _method
 
-__all__ = ["ftle_grid_2D", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D",
+__all__ = ["ftle_grid_2D", "ftle_grid_2D_series", "ftle_slab_2D", "lavd_grid_2D", "flowmap_ftle_grid_2D",
            "lavd_flowmap_grid_2D", "lavd_vort_sums", "C_tensor_2D", "C_eig_aux_2D", "C_eig_2D", "ftle_from_eig"]
 
 
@@ -31,6 +31,20 @@ def ftle_grid_2D(flowmap, T, dx, dy, mask=None, *, device_out=False):
     out = _lib.alloc_out((nx, ny), np.float64, dev)
     _lib.check(_lib.load().b200cs_ftle_grid_2d(fm.ptr, nx, ny, float(T), float(dx), float(dy),
                                                ma.ptr, out.ptr, _lib.current_stream(dev)))
+    return out.obj
+
+
+def ftle_grid_2D_series(flowmaps, T, dx, dy, mask=None, *, device_out=False):
+    """ftle_grid_2D on every frame of flowmaps (nt, nx, ny, 2) -> (nt, nx, ny), one launch; frame f
+    is bit-identical to ftle_grid_2D(flowmaps[f], T, dx, dy, mask)."""
+    fm, ma = _lib.arg_in(flowmaps), _lib.mask_in(mask)
+    if fm.obj.ndim != 4 or fm.obj.shape[3] != 2:
+        raise ValueError("flowmaps must have shape (nt, nx, ny, 2)")
+    nt, nx, ny = (int(v) for v in fm.obj.shape[:3])
+    dev = bool(device_out or fm.on_device)
+    out = _lib.alloc_out((nt, nx, ny), np.float64, dev)
+    _lib.check(_lib.load().b200cs_ftle_series_2d(fm.ptr, nt, nx, ny, float(T), float(dx), float(dy),
+                                                 ma.ptr, out.ptr, _lib.current_stream(dev)))
     return out.obj
 
 

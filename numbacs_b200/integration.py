@@ -21,7 +21,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D",
-           "flowmap_grid_ND", "flowmap_n_grid_ND",
+           "flowmap_grid_ND", "flowmap_n_grid_ND", "flowmap_grid_2D_series",
            "flowmap_composition", "flowmap_composition_initial", "flowmap_composition_step"]
 
 
@@ -134,6 +134,41 @@ def flowmap_aux_grid_2D(funcptr, t0, T, x, y, params, h=1e-5, eig_main=True, com
     return out.obj
 
 
+def flowmap_grid_2D_series(funcptr, t0s, T, x, y, params, method="dop853", rtol=1e-6, atol=1e-8,
+                           mask=None, *, device_out=False, info=None, out=None):
+    """flowmap_grid_2D for a whole series of initial times in ONE launch -> (nt, nx, ny, 2).
+
+    Frame f is bit-identical to flowmap_grid_2D(funcptr, t0s[f], T, x, y, params, ...).  An FTLE
+    movie frame (201 x 101 in the reference's time-series examples) is far too small to fill the
+    GPU; the batch is what does.  `out` (optional) is a preallocated (nt, nx, ny, 2) float64 numpy
+    array or CUDA tensor to write into."""
+    xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
+    ta = _lib.arg_in(np.atleast_1d(t0s) if not _lib._is_torch(t0s) else t0s)
+    nt, nx, ny = int(ta.obj.shape[0]), int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    if ma.obj is not None and tuple(ma.obj.shape) != (nx, ny):
+        raise ValueError(f"mask must have shape {(nx, ny)}")
+    if out is not None:
+        if tuple(int(v) for v in out.shape) != (nt, nx, ny, 2):
+            raise ValueError(f"out must have shape {(nt, nx, ny, 2)}")
+        on_dev = _lib._is_torch(out)
+        if on_dev and not (out.is_cuda and out.is_contiguous() and str(out.dtype) == "torch.float64"):
+            raise ValueError("out must be a contiguous float64 CUDA tensor")
+        if not on_dev and not (out.dtype == np.float64 and out.flags.c_contiguous):
+            raise ValueError("out must be a C-contiguous float64 array")
+        res = _lib.Arg(out, C.c_void_p(out.data_ptr() if on_dev else out.ctypes.data), on_dev)
+        dev = on_dev
+    else:
+        dev = bool(device_out or xa.on_device or ya.on_device or ma.on_device or ta.on_device)
+        res = _lib.alloc_out((nt, nx, ny, 2), np.float64, dev)
+    status, steps, stats = _info_bufs(info, (nt, nx, ny), dev)
+    _lib.check(_lib.load().b200cs_flowmap_grid_2d_series(
+        int(funcptr), ta.ptr, nt, float(T), xa.ptr, nx, ya.ptr, ny, pa.ptr, int(pa.obj.shape[0]),
+        _method(method), float(rtol), float(atol), ma.ptr, res.ptr, status.ptr, steps.ptr, stats.ptr,
+        _lib.current_stream(dev)))
+    _fill_info(info, status, steps, stats)
+    return res.obj
+
+
 def _flat_points(IC_flat, ndims):
     """IC_flat (npts * ndims,) -> (npts, ndims) view: particle k is IC_flat[k*ndims:(k+1)*ndims]
     (integration.py:224, 586), i.e. exactly the row-major point list the pts kernels take."""
@@ -213,9 +248,12 @@ def flowmap_composition_initial(funcptr, t0, T, h, x, y, grid, params, *, device
     nx, ny = int(grid[0][2]), int(grid[1][2])
     dev = bool(device_out or _lib._is_torch(x) and x.is_cuda)
     flowmaps = _new_flowmaps(nT, nx, ny, dev)
-    for k in range(nT):
-        _flowmap_into(flowmaps[k], funcptr, t0, h, x, y, params, kwargs)
+    t0s = np.empty(nT, np.float64)
+    for k in range(nT):            # the reference's running sum t0 += h (integration.py:686-688)
+        t0s[k] = t0
         t0 += h
+    if nT:
+        flowmap_grid_2D_series(funcptr, t0s, h, x, y, params, out=flowmaps, **kwargs)
     return flowmap_composition(flowmaps, grid, nT, device_out=dev), flowmaps, nT
 
 

@@ -407,3 +407,41 @@ def test_edge_cases_of_the_tensor_and_ridge_entries(nb, oracle):
         I.flowmap_composition(np.zeros((3, 5, 5, 2)), ((0, 1, 5), (0, 1, 6)), 3)
     with pytest.raises(NotImplementedError):
         I.flowmap_aux_grid_2D(f, 0.0, 1.0, x, y, p, method="lsoda")
+
+
+# ------------------------------------------------------------------ time series in one launch
+
+def test_flowmap_and_ftle_series_equal_the_per_frame_calls(nb):
+    import torch
+    I, D = nb.integration, nb.diagnostics
+    x, y = np.linspace(0, 2, 67), np.linspace(0, 1, 35)
+    dx, dy = x[1] - x[0], y[1] - y[0]
+    t0s = np.array([0.0, 0.5, 3.25, 7.0, -2.0])
+    rng = np.random.default_rng(8)
+    mask = rng.random((67, 35)) < 0.1
+    for direction, T in ((1.0, 6.0), (-1.0, -6.0)):
+        f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=direction)
+        info = {}
+        fms = I.flowmap_grid_2D_series(f, t0s, T, x, y, p, mask=mask, info=info)
+        assert fms.shape == (5, 67, 35, 2) and info["status"].shape == (5, 67, 35)
+        fts = D.ftle_grid_2D_series(fms, T, dx, dy, mask=mask)
+        tot = np.zeros(3, np.int64)
+        for k, t0 in enumerate(t0s):
+            one = {}
+            fm = I.flowmap_grid_2D(f, t0, T, x, y, p, mask=mask, info=one)
+            assert np.array_equal(fms[k], fm) and np.array_equal(info["steps"][k], one["steps"])
+            assert np.array_equal(fts[k], D.ftle_grid_2D(fm, T, dx, dy, mask=mask))
+            tot += one["stats"]
+        assert np.array_equal(info["stats"], tot)
+    # device-resident, other flows, writing into a preallocated tensor
+    fb, pb, dom = nb.flows.get_predefined_flow("bickley_jet")
+    xb = torch.linspace(dom[0][0], dom[0][1], 50, dtype=torch.float64, device="cuda")
+    yb = torch.linspace(-3, 3, 30, dtype=torch.float64, device="cuda")
+    out = torch.empty((3, 50, 30, 2), dtype=torch.float64, device="cuda")
+    res = I.flowmap_grid_2D_series(fb, [0.0, 1.0, 2.0], 3.0, xb, yb, pb, out=out)
+    assert res is out
+    for k in range(3):
+        assert torch.equal(out[k], I.flowmap_grid_2D(fb, float(k), 3.0, xb, yb, pb))
+    assert I.flowmap_grid_2D_series(fb, np.zeros(0), 3.0, xb, yb, pb).shape == (0, 50, 30, 2)
+    with pytest.raises(ValueError):
+        I.flowmap_grid_2D_series(fb, [0.0], 3.0, xb, yb, pb, out=torch.empty((2, 50, 30, 2), dtype=torch.float64, device="cuda"))
