@@ -302,6 +302,13 @@ B200CS_API int b200cs_flowmap_composition(const double *flowmaps, const double *
 B200CS_API int b200cs_binary_mask_dilation(const uint8_t *mask, int64_t nx, int64_t ny, int corners,
                                 uint8_t *dilated, void *stream);
 
+/* The whole composition time series in one launch: flowmaps is [nT + nframes - 1, nx, ny, 2]
+ * (consecutive intervals of length h), frame f composes maps f .. f + nT - 1 exactly like
+ * b200cs_flowmap_composition -- what flowmap_composition_step produces frame by frame
+ * (integration.py:691-737).  composed is [nframes, nx, ny, 2]. */
+B200CS_API int b200cs_flowmap_composition_series(const double *flowmaps, const double *grid6, int64_t nT,
+                                      int64_t nframes, double *composed, void *stream);
+
 /* out2 = { sorted(data)[k], sorted(data)[min(k+1, n-1)] } by radix select (no sort, data is not
  * modified): the two order statistics np.percentile interpolates between (ridges.py:45, 279). */
 B200CS_API int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream);

@@ -63,6 +63,7 @@ PROTOTYPES = {
                            _vp],
     "b200cs_flowmap_composition": [_vp, _vp, _i64, _vp, _vp],
     "b200cs_binary_mask_dilation": [_vp, _i64, _i64, _i, _vp, _vp],
+    "b200cs_flowmap_composition_series": [_vp, _vp, _i64, _i64, _vp, _vp],
     "b200cs_order_stats": [_vp, _i64, _i64, _vp, _vp],
     "b200cs_fp64_peak": [_i, C.POINTER(_d), C.POINTER(_d)],
 }

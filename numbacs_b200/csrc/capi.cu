@@ -1013,6 +1013,31 @@ int b200cs_binary_mask_dilation(const uint8_t *mask, int64_t nx, int64_t ny, int
     });
 }
 
+int b200cs_flowmap_composition_series(const double *flowmaps, const double *grid6, int64_t nT, int64_t nframes,
+                                      double *composed, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmaps && grid6 && composed, "null argument");
+        B2_REQUIRE(nT >= 1 && nframes >= 0, "nT must be >= 1 and nframes >= 0");
+        if (nframes == 0) return;
+        double g[6];
+        B2_CHECK_CUDA(cudaMemcpy(g, grid6, sizeof(g), cudaMemcpyDefault));
+        const long long nx = (long long)g[2], ny = (long long)g[5];
+        B2_REQUIRE(nx >= 2 && ny >= 2, "the grid needs at least 2 points per axis");
+        B2_REQUIRE(g[1] > g[0] && g[4] > g[3], "grid axes must be ascending");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmaps, np * 2 * (size_t)(nT + nframes - 1), s);
+        Out<double> dout(composed, np * 2 * (size_t)nframes, s);
+        for (int64_t f0 = 0; f0 < nframes; f0 += 65535) {
+            const int64_t nf = (nframes - f0 < 65535) ? nframes - f0 : 65535;
+            launch_composition(dfm.dev + f0 * np * 2, g, nT, dout.dev + f0 * np * 2, s, nf);
+        }
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int b200cs_order_stats(const double *data, int64_t n, int64_t k, double *out2, void *stream) {
     return guarded([&] {
         require_device();

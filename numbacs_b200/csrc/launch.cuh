@@ -88,7 +88,7 @@ void launch_ridge_components(const double *f, const double *ev, long long ev_pix
                              double *pts_compact, long long *roots_compact, long long capacity,
                              long long *count, cudaStream_t s);
 void launch_composition(const double *flowmaps, const double *grid6 /*host*/, long long nT, double *out,
-                        cudaStream_t s);
+                        cudaStream_t s, long long frames = 1);
 void launch_mask_dilation(const uint8_t *mask, long long nx, long long ny, bool corners, uint8_t *out,
                           cudaStream_t s);
 void launch_order_stats(const double *data, long long n, long long k, double *out2, cudaStream_t s);

@@ -478,6 +478,9 @@ composition_kernel(const double2 *__restrict__ fms, const __grid_constant__ Grid
     const long long np = (long long)g.n[0] * g.n[1];
     const long long q = (long long)blockIdx.x * kTB + threadIdx.x;
     if (q >= np) return;
+    // blockIdx.y = frame of a sliding window: frame f composes maps f .. f + nT - 1
+    fms += (long long)blockIdx.y * np;
+    out += (long long)blockIdx.y * np;
     double2 p = __ldg(fms + q);
     for (long long k = 1; k < nT - 1; ++k) p = bilinear2(g, fms + k * np, p.x, p.y);
     out[q] = bilinear2(g, fms + (nT - 1) * np, p.x, p.y);
@@ -696,7 +699,9 @@ void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stri
     }
 }
 
-void launch_composition(const double *flowmaps, const double *grid6, long long nT, double *out, cudaStream_t s) {
+void launch_composition(const double *flowmaps, const double *grid6, long long nT, double *out, cudaStream_t s,
+                        long long frames) {
+    B2_REQUIRE(frames >= 1 && frames <= 65535, "1 .. 65535 frames per composition launch (got %lld)", frames);
     B2_REQUIRE((reinterpret_cast<uintptr_t>(flowmaps) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                "flow maps must be 16-byte aligned");
     Grid2 g{};
@@ -707,7 +712,7 @@ void launch_composition(const double *flowmaps, const double *grid6, long long n
         g.delta[d] = (g.b[d] - g.a[d]) / (double)(g.n[d] - 1);
         g.inv_delta[d] = 1.0 / g.delta[d];
     }
-    composition_kernel<<<blocks_for((long long)g.n[0] * g.n[1]), kTB, 0, s>>>(
+    composition_kernel<<<dim3(blocks_for((long long)g.n[0] * g.n[1]), (unsigned)frames), kTB, 0, s>>>(
         reinterpret_cast<const double2 *>(flowmaps), g, nT, reinterpret_cast<double2 *>(out));
     B2_CHECK_CUDA(cudaGetLastError());
 }

@@ -22,7 +22,8 @@ from . import _lib
 
 __all__ = ["flowmap", "flowmap_n", "flowmap_grid_2D", "flowmap_n_grid_2D", "flowmap_aux_grid_2D",
            "flowmap_grid_ND", "flowmap_n_grid_ND", "flowmap_grid_2D_series",
-           "flowmap_composition", "flowmap_composition_initial", "flowmap_composition_step"]
+           "flowmap_composition", "flowmap_composition_initial", "flowmap_composition_step",
+           "flowmap_composition_series"]
 
 
 def _method(method):
@@ -270,3 +271,32 @@ def flowmap_composition_step(flowmaps, funcptr, t0, h, nT, x, y, grid, params, *
         flowmaps[:-1] = flowmaps[1:].copy()
     _flowmap_into(flowmaps[-1], funcptr, t0, h, x, y, params, kwargs)
     return flowmap_composition(flowmaps, grid, nT), flowmaps
+
+
+def flowmap_composition_series(funcptr, t0, T, h, n, x, y, grid, params, *, device_out=False, **kwargs):
+    """The n composed flow maps that flowmap_composition_initial followed by n - 1 calls of
+    flowmap_composition_step produce (frame k covers [t0 + k h, t0 + k h + T]) -> (n, nx, ny, 2),
+    in TWO launches: every intermediate map of every frame from one time-series integration
+    (nT + n - 1 maps, each over one interval h), then one sliding-window composition kernel.
+    The interval start times are the running sums t0, t0 + h, (t0 + h) + h, ... of the reference's
+    loop, so frame 0 equals flowmap_composition_initial's result bit for bit."""
+    nT = abs(round(T / h))
+    nx, ny = int(grid[0][2]), int(grid[1][2])
+    if nT < 1 or n < 1:
+        raise ValueError("need at least one intermediate map and one frame")
+    dev = bool(device_out or _lib._is_torch(x) and x.is_cuda)
+    nmaps = nT + int(n) - 1
+    t0s = np.empty(nmaps, np.float64)
+    t = t0
+    for k in range(nT):                  # flowmap_composition_initial: t0 += h per map
+        t0s[k] = t
+        t += h
+    for k in range(1, int(n)):           # step k integrates from t0 + T + (k - 1) h in the examples
+        t0s[nT + k - 1] = t0 + T + (k - 1) * h
+    flowmaps = flowmap_grid_2D_series(funcptr, t0s, h, x, y, params, device_out=dev, **kwargs)
+    g = _grid6(grid)
+    out = _lib.alloc_out((int(n), nx, ny, 2), np.float64, dev)
+    fa = _lib.arg_in(flowmaps)
+    _lib.check(_lib.load().b200cs_flowmap_composition_series(fa.ptr, C.c_void_p(g.ctypes.data), nT, int(n),
+                                                             out.ptr, _lib.current_stream(dev)))
+    return out.obj

@@ -445,3 +445,23 @@ def test_flowmap_and_ftle_series_equal_the_per_frame_calls(nb):
     assert I.flowmap_grid_2D_series(fb, np.zeros(0), 3.0, xb, yb, pb).shape == (0, 50, 30, 2)
     with pytest.raises(ValueError):
         I.flowmap_grid_2D_series(fb, [0.0], 3.0, xb, yb, pb, out=torch.empty((2, 50, 30, 2), dtype=torch.float64, device="cuda"))
+
+
+def test_flowmap_composition_series_equals_initial_plus_steps(nb):
+    import torch
+    I = nb.integration
+    nx, ny, n = 81, 41, 7
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    grid = ((x[0], x[-1], nx), (y[0], y[-1], ny))
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    t0, T, h = 0.5, 6.0, 1.5
+    series = I.flowmap_composition_series(f, t0, T, h, n, x, y, grid, p)
+    assert series.shape == (n, nx, ny, 2)
+    fm0, fms, nT = I.flowmap_composition_initial(f, t0, T, h, x, y, grid, p)
+    assert nT == 4 and np.array_equal(series[0], fm0)
+    for k in range(1, n):
+        fmk, fms = I.flowmap_composition_step(fms, f, t0 + T + (k - 1) * h, h, nT, x, y, grid, p)
+        assert np.array_equal(series[k], fmk)
+    xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    sd = I.flowmap_composition_series(f, t0, T, h, n, xd, yd, grid, p)
+    assert sd.is_cuda and np.array_equal(sd.cpu().numpy(), series)

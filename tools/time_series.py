@@ -4,13 +4,14 @@ gyre 201 x 101, T = 16, n = 200 frames one time unit apart), device-resident, CU
   loop     : flowmap_grid_2D + ftle_grid_2D per frame (what the example's "standard" branch does)
   batched  : flowmap_grid_2D_series + ftle_grid_2D_series, all frames in one launch each
   composed : flowmap_composition_initial + n-1 flowmap_composition_step (+ ftle per frame)
+  composed_batched : flowmap_composition_series + ftle_grid_2D_series (three launches in total)
     python tools/time_series.py [nx=201] [ny=101] [n=200]  -> one JSON line"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from numbacs_b200.flows import get_predefined_flow
 from numbacs_b200.integration import (flowmap_grid_2D, flowmap_grid_2D_series, flowmap_composition_initial,
-                                      flowmap_composition_step)
+                                      flowmap_composition_step, flowmap_composition_series)
 from numbacs_b200.diagnostics import ftle_grid_2D, ftle_grid_2D_series
 
 nx = int(sys.argv[1]) if len(sys.argv) > 1 else 201
@@ -53,12 +54,18 @@ def composed():
     return torch.stack(out)
 
 
+def composed_batched():
+    return ftle_grid_2D_series(flowmap_composition_series(f, t0, T, h, n, x, y, grid, p), T, dx, dy)
+
+
 t_loop, a = timed(loop)
 t_bat, b = timed(batched)
 t_comp, c = timed(composed)
+t_cb, d = timed(composed_batched)
 pts = n * nx * ny
 print(json.dumps({"grid": [nx, ny], "frames": n, "T": T,
                   "loop_ms": t_loop, "batched_ms": t_bat, "composed_ms": t_comp,
                   "loop_Mpts_per_s": pts / t_loop / 1e3, "batched_Mpts_per_s": pts / t_bat / 1e3,
+                  "composed_batched_ms": t_cb, "composed_batched_equals_composed": bool(torch.equal(c, d)),
                   "batched_equals_loop": bool(torch.equal(a, b)),
                   "composed_vs_direct_median_abs_ftle_diff": float((c - a).abs().median())}))
