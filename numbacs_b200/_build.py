@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libb200cs.so")
 
-SOURCES = ["capi.cu", "flowmap_dispatch.cu", "flowmap_dg.cu", "flowmap_bickley.cu",
+SOURCES = ["capi.cu", "flowmap_dispatch.cu", "flowmap_dg.cu", "flowmap_dg_damped.cu", "flowmap_bickley.cu",
            "flowmap_abc.cu", "flowmap_spline.cu", "flowmap_linear.cu", "ftle_kernels.cu", "diag_kernels.cu",
            "tensor_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",

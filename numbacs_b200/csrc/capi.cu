@@ -108,6 +108,14 @@ static void read_params(const double *params, int nparams, int min_params, RhsPa
 }
 
 static void fill_rhs(const FlowSpec &f, RhsParams &R) {
+    for (double &d : R.d) d = 0.0;
+    if (f.kind == B200CS_FLOW_DOUBLE_GYRE) {
+        // constants of the double-gyre RHS folded once here (the same IEEE operations the kernel
+        // used to repeat in every stage): see DoubleGyreT in flows.cuh
+        R.d[0] = R.p[4] * R.p[0];                                // omega * p0
+        R.d[1] = (0.5 * (3.141592653589793 * R.p[1])) * R.p[0];  // p0 * pi * A / 2
+        R.d[2] = -(R.p[3] * R.p[0]);                             // -p0 * alpha
+    }
     R.coef_uv = nullptr;
     R.r = f.r;
     std::memset(&R.grid, 0, sizeof(R.grid));

@@ -34,6 +34,9 @@
 
 #include "dop853_tableau.cuh"
 
+#ifndef B200CS_LEAN
+#define B200CS_LEAN 1
+#endif
 #ifndef B200CS_SYNC_EVERY
 #define B200CS_SYNC_EVERY 8
 #endif
@@ -228,7 +231,12 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             double e3 = fma(-dop::kTab.bhh[0], K[1][i], s);
             e3 = fma(-dop::kTab.bhh[1], K[9][i], e3);
             e3 = fma(-dop::kTab.bhh[2], K[12][i], e3);
+#if B200CS_LEAN
+            const double rsk = 1.0 / sk;  // one reciprocal serves both estimates (<= 1 ulp from e/sk)
+            e3 *= rsk;
+#else
             e3 /= sk;
+#endif
             err2 = fma(e3, e3, err2);
             double e5 = dop::kTab.er[1] * K[1][i];
             e5 = fma(dop::kTab.er[6], K[6][i], e5);
@@ -238,12 +246,20 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             e5 = fma(dop::kTab.er[10], K[10][i], e5);
             e5 = fma(dop::kTab.er[11], K[11][i], e5);
             e5 = fma(dop::kTab.er[12], K[12][i], e5);
+#if B200CS_LEAN
+            e5 *= rsk;
+#else
             e5 /= sk;
+#endif
             err = fma(e5, e5, err);
         }
         double deno = fma(0.01, err2, err);
         if (deno <= 0.0) deno = 1.0;
+#if B200CS_LEAN
+        err = fabs(h) * err * rsqrt(deno * (double)N);
+#else
         err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
+#endif
         const double fac11 = detail::pow_eighth(err);
         const double fac = fmax(kFacc2, fmin(kFacc1, fac11 / kSafe));  // beta = 0
         double hnew = h / fac;

@@ -153,6 +153,129 @@ __device__ __forceinline__ void sinpi_v(const double (&u)[M], double (&s)[M]) {
     }
 }
 
+// ---- "wide" kernels: ONE odd polynomial on the whole half period ------------------------------
+// The parity-selected kernels above need, per sine, six per-lane indexed constant loads (LDC), four
+// FSEL and a handful of LOP3/SHL for the index and the select -- ~15 issue slots next to 13 FP64
+// instructions, on a kernel whose issue port is as loaded as its FP64 pipe.  Reducing only to
+// |r| <= 1/2 (in units of pi) leaves a single sign flip: sin(pi u) = (-1)^k sin(pi r), k = rint(u),
+// r = u - k exact.  The price is a degree-17 odd polynomial instead of degree 13: +1 FP64
+// instruction per sine, but every coefficient is a warp-uniform LDCU shared by all M chains.
+// Coefficients: Chebyshev-node interpolation of (sin(pi r)/r - pi)/r^2 on r^2 in [0, 1/4] and of
+// (sin r / r - 1)/r^2 on [0, (pi/2)^2], computed with 60-digit arithmetic (tools/fit_trig_poly.py);
+// measured error <= 1.5 ulp on 2e5 random arguments.
+struct __align__(16) WideTrigConsts {
+    double magic;        // 1.5 * 2^52
+    double pi_hi, pi_lo; // pi = pi_hi + pi_lo
+    double inv_pi;
+    double cp[8];        // sin(pi r) = r pi_hi + r (pi_lo + z (cp0 + z cp1 + ... + z^7 cp7)), z = r^2
+    double cs[8];        // sin(r)    = r + r z (cs0 + z cs1 + ... + z^7 cs7)
+};
+
+static __constant__ WideTrigConsts kWide = {
+    6755399441055744.0,
+    3.141592653589793, 1.2246467991473532e-16,
+    0.3183098861837907,
+    {-5.16771278004997, 2.55016403987734, -0.599264529320343, 0.08214588659675232,
+     -0.007370430719634586, 0.00046630087411496363, -2.1906201655131958e-05, 7.725743030789876e-07},
+    {-0.16666666666666666, 0.008333333333333316, -0.00019841269841254966, 2.7557319219160833e-06,
+     -2.505210761669045e-08, 1.6058977292642743e-10, -7.643969663988074e-13, 2.7314368769379893e-15}};
+
+// s[m] = sin(pi u[m]), wide kernel
+template <int M>
+__device__ __forceinline__ void sinpi_wide_v(const double (&u)[M], double (&s)[M]) {
+    bool slow = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) slow |= !trig_in_range(u[m]);
+    if (slow) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) s[m] = sincos_slow(3.141592653589793 * u[m]).x;
+        return;
+    }
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = u[m] + kWide.magic;
+        q[m] = __double2loint(t);
+        r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+        z[m] = r[m] * r[m];
+        p[m] = kWide.cp[7];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        p[m] = fma(p[m], z[m], kWide.pi_lo);
+        s[m] = flip_sign(fma(r[m], kWide.pi_hi, r[m] * p[m]), q[m] & 1);
+    }
+}
+
+// Branch-free form of sinpi_wide_v.  The reduction above is exact for every |u| < 2^51 (t = u + magic
+// has ulp 1 there), so no libm fall-back is needed below that; NaN and +-inf produce NaN through
+// r = u - k by themselves.  What is left are finite |u| >= 2^51: every such double is a multiple
+// of 1/2 (of 1 from 2^52 on, where sin(pi u) = +-0 exactly) and its own rounding error is a
+// quarter period or more, so the value is meaningless; r is forced to 0 there so that the result
+// is a clean 0 instead of a polynomial evaluated far outside its interval.  Without the branch
+// (and its convergence barrier) a whole step attempt of the double-gyre kernel is one basic
+// block, which lets ptxas start the next stage's a_sj K_j sums under the polynomial chains.
+template <int M>
+__device__ __forceinline__ void sinpi_wide_nobranch_v(const double (&u)[M], double (&s)[M]) {
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = u[m] + kWide.magic;
+        q[m] = __double2loint(t);
+        r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+        // finite and >= 2^51 (high word in [0x43200000, 0x7ff00000)): unsigned wrap-around compare
+        const unsigned d = (unsigned)(__double2hiint(u[m]) & 0x7fffffff) - 0x43200000u;
+        if (d < 0x3cd00000u) r[m] = 0.0;
+        z[m] = r[m] * r[m];
+        p[m] = kWide.cp[7];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        p[m] = fma(p[m], z[m], kWide.pi_lo);
+        s[m] = flip_sign(fma(r[m], kWide.pi_hi, r[m] * p[m]), q[m] & 1);
+    }
+}
+
+// s[m] = sin(x[m]), wide kernel (|x| < 1e5, else libm)
+template <int M>
+__device__ __forceinline__ void sin_wide_v(const double (&x)[M], double (&s)[M]) {
+    bool slow = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) slow |= !trig_in_range(x[m]);
+    if (slow) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) s[m] = sincos_slow(x[m]).x;
+        return;
+    }
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = fma(x[m], kWide.inv_pi, kWide.magic);
+        q[m] = __double2loint(t);
+        const double k = t - kWide.magic;
+        r[m] = fma(-k, kWide.pi_lo, fma(-k, kWide.pi_hi, x[m]));  // two-term Cody-Waite by pi
+        z[m] = r[m] * r[m];
+        p[m] = kWide.cs[7];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cs[k]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) s[m] = flip_sign(fma(r[m] * z[m], p[m], r[m]), q[m] & 1);
+}
+
 __device__ __forceinline__ double sin_fast(double x) {
     const double a[1] = {x};
     double s[1];

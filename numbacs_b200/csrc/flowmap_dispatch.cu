@@ -71,7 +71,10 @@ void launch_rhs_eval(const FlowSpec &f, const RhsParams &P, const double *t, con
     const unsigned g = (unsigned)((npts + b - 1) / b);
     if (!g) return;
     switch (f.kind) {
-    case B200CS_FLOW_DOUBLE_GYRE: rhs_kernel<DoubleGyre><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
+    case B200CS_FLOW_DOUBLE_GYRE:
+        if (P.p[3] != 0.0) rhs_kernel<DoubleGyreDamped><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        else rhs_kernel<DoubleGyre><<<g, b, 0, s>>>(P, t, y, npts, dy);
+        break;
     case B200CS_FLOW_BICKLEY_JET: rhs_kernel<BickleyJet><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
     case B200CS_FLOW_ABC: rhs_kernel<Abc><<<g, b, 0, s>>>(P, t, y, npts, dy); break;
     case B200CS_FLOW_SPLINE2D:

@@ -32,11 +32,17 @@ struct KernelShape {
 #ifndef B200CS_DG_THREADS
 #define B200CS_DG_THREADS 640
 #endif
-template <>
-struct KernelShape<DoubleGyre, false> {
+#ifndef B200CS_DG_LOCKSTEP
+#define B200CS_DG_LOCKSTEP true
+#endif
+#ifndef B200CS_DG_MINBLOCKS
+#define B200CS_DG_MINBLOCKS 1
+#endif
+template <bool DAMPED>
+struct KernelShape<DoubleGyreT<DAMPED>, false> {
     static constexpr int kThreads = B200CS_DG_THREADS;
-    static constexpr int kMinBlocks = 1;
-    static constexpr bool kLockstep = true;
+    static constexpr int kMinBlocks = B200CS_DG_MINBLOCKS;
+    static constexpr bool kLockstep = B200CS_DG_LOCKSTEP;
 };
 #ifndef B200CS_SPLINE_THREADS
 #define B200CS_SPLINE_THREADS 512

@@ -31,25 +31,47 @@ struct RhsParams {
     SplineGridDev grid;       // Spline2D only
     const double2 *coef_uv;   // Spline2D only
     double r;                 // Spline2D spherical radius
+    double d[4];              // constants derived from p on the host (derive_rhs, capi.cu)
 };
 
-struct DoubleGyre {
+#ifndef B200CS_LEAN
+#define B200CS_LEAN 1
+#endif
+#ifndef B200CS_SINPI_WIDE
+#define B200CS_SINPI_WIDE 1
+#endif
+#ifndef B200CS_SIN_WIDE
+#define B200CS_SIN_WIDE 1
+#endif
+
+// DAMPED = false is the flow with alpha == 0 (the default parameters, and every example of the
+// reference): the launcher picks the instantiation, so the hot loop carries neither the damping
+// terms nor a test for them.
+template <bool DAMPED>
+struct DoubleGyreT {
     static constexpr int N = 2;
     static constexpr int kAux = 1;
     const RhsParams &P;
-    __device__ __forceinline__ explicit DoubleGyre(const RhsParams &P_) : P(P_) {}
+    __device__ __forceinline__ explicit DoubleGyreT(const RhsParams &P_) : P(P_) {}
 
     // a(t) = eps * sin(omega*tt + psi), tt = p0*t   (flows.py:1152-1153).
     // p[0] is the integration direction, +-1 (userguide.rst:217-227), so folding it into omega
-    // (and into the amplitudes below) is an exact sign change, not a rounding.
+    // (and into the amplitudes below) is an exact sign change, not a rounding.  The folded
+    // constants are formed once on the host (derive_rhs in capi.cu): P.d[0] = omega*p0,
+    // P.d[1] = p0*pi*A/2, P.d[2] = -p0*alpha -- one LDCU each instead of being re-derived from
+    // the constant bank in every stage.
     template <int M>
     __device__ __forceinline__ void time_part(const double (&t)[M], double (&aux)[M]) const {
         const double eps = P.p[2], psi = P.p[5];
-        const double omega_p0 = P.p[4] * P.p[0];
+        const double omega_p0 = P.d[0];
         double arg[M], sa[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) arg[m] = fma(omega_p0, t[m], psi);
+#if B200CS_SIN_WIDE
+        sin_wide_v<M>(arg, sa);
+#else
         sin_v<M>(arg, sa);
+#endif
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = eps * sa[m];
     }
@@ -63,10 +85,13 @@ struct DoubleGyre {
     // differences), both forms vanish exactly on the walls x = 0 and y = 0, and the parity tests
     // (step-count equality, 1e-8 x domain) are the guard.
     __device__ __forceinline__ void eval(double a, double /*t*/, const double (&y)[2], double (&dy)[2]) const {
-        const double c = (0.5 * (kPi * P.p[1])) * P.p[0];  // p0 * pi*A/2 (exact scalings of pi*A)
-        const double damp = -(P.p[3] * P.p[0]);            // -p0*alpha, 0 for the default flow
+        const double c = P.d[1];     // p0 * pi*A/2 (exact scalings of pi*A)
         const double b = 1.0 - 2.0 * a;
+#if B200CS_LEAN
+        const double f = y[0] * fma(a, y[0], b);         // a*y0**2 + b*y0, one instruction fewer
+#else
         const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
+#endif
         const double df = fma(2.0 * a, y[0], b);
         double s[2];
 #ifdef B200CS_DG_NO_SINPI
@@ -74,9 +99,16 @@ struct DoubleGyre {
         sin_v<2>(arg, s);
 #else
         const double arg[2] = {f + y[1], f - y[1]};
+#if B200CS_SINPI_WIDE == 2
+        sinpi_wide_nobranch_v<2>(arg, s);
+#elif B200CS_SINPI_WIDE
+        sinpi_wide_v<2>(arg, s);
+#else
         sinpi_v<2>(arg, s);  // sin(pi (f +- y)) with an exact argument reduction
 #endif
-        if (damp != 0.0) {
+#endif
+        if (DAMPED) {
+            const double damp = P.d[2];  // -p0*alpha
             dy[0] = fma(-c, s[0] + s[1], damp * y[0]);
             dy[1] = fma(c * (s[0] - s[1]), df, damp * y[1]);
         } else {
@@ -85,6 +117,8 @@ struct DoubleGyre {
         }
     }
 };
+using DoubleGyre = DoubleGyreT<false>;
+using DoubleGyreDamped = DoubleGyreT<true>;
 
 struct BickleyJet {
     static constexpr int N = 2;

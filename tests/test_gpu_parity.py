@@ -242,6 +242,38 @@ def test_double_gyre_C1(nb, oracle):
     assert np.array_equal(fm2, fm) and np.array_equal(ft2, ft)
 
 
+def test_double_gyre_damped(nb, lib, oracle):
+    """alpha != 0 (flows.py:1157-1158, the -alpha*y terms) and psi != 0 run the DoubleGyreDamped
+    instantiation: RHS at a few ulp of the velocity scale, flow map within 1e-8 x domain."""
+    rng = np.random.default_rng(11)
+    for direction in (1.0, -1.0):
+        f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=direction)
+        fo, po, _ = oracle.get_predefined_flow("double_gyre", int_direction=direction)
+        p = p.copy()
+        p[3], p[5] = 0.07, 0.3
+        yy = rng.uniform((0, 0), (2, 1), size=(2000, 2))
+        tt = rng.uniform(-10, 10, size=2000)
+        g = _gpu_rhs(lib, f, tt, yy, p)
+        o = np.array([fo.rhs(tt[i], yy[i], p) for i in range(len(tt))])
+        assert np.abs(g - o).max() <= 1e-14 * np.abs(o).max()
+        x, y = np.linspace(0, 2, 101), np.linspace(0, 1, 51)
+        info = {}
+        fm = nb.integration.flowmap_grid_2D(f, 0.0, direction * 6.0, x, y, p, info=info)
+        fmo, _, st_o, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, direction * 6.0, x, y, p, full=True)
+        r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
+        assert (info["status"] == 1).all()
+        assert r["max_match"] <= 1e-8 and r["mismatch"] <= 1e-3 * r["n"] + 4, r
+        assert r["p99"] <= 1e-8, r
+        # the undamped instantiation is the alpha -> 0 limit of the damped one
+        p0 = p.copy()
+        p0[3] = 0.0
+        pe = p.copy()
+        pe[3] = 1e-300
+        a = nb.integration.flowmap_grid_2D(f, 0.0, direction * 6.0, x, y, p0)
+        b = nb.integration.flowmap_grid_2D(f, 0.0, direction * 6.0, x, y, pe)
+        assert np.abs(a - b).max() <= 1e-12
+
+
 def _noise_floor(oracle, flow_o, t0, T, x, y, p, L, k=None, flow_o2=None):
     """How much the oracle moves under a 1-ulp perturbation (of params[k], or of the coefficient
     arrays behind flow_o2), over particles whose step counts stay equal."""
