@@ -37,6 +37,9 @@
 #ifndef B200CS_LEAN
 #define B200CS_LEAN 1
 #endif
+#ifndef B200CS_LEAN2
+#define B200CS_LEAN2 B200CS_LEAN
+#endif
 #ifndef B200CS_SYNC_EVERY
 #define B200CS_SYNC_EVERY 8
 #endif
@@ -53,7 +56,20 @@ namespace detail {
 
 // err^(1/8) with three correctly rounded square roots (libm pow in the reference; the difference
 // is <= 1 ulp and only scales the next step size)
+#if B200CS_LEAN2
+// three square roots as x * rsqrt(x) (MUFU seed + one Newton step each, <= 2 ulp; x > 0 here or the
+// result is only compared / clamped) instead of three correctly rounded ones
+__device__ __forceinline__ double sqrt_fast(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
+__device__ __forceinline__ double pow_eighth(double x) { return sqrt_fast(sqrt_fast(sqrt_fast(x))); }
+#else
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
+#endif
+// a / c for a compile-time constant c: q = a*rc, one FMA residual correction -> the correctly
+// rounded quotient in 3 FP64 instructions (see tensor_kernels.cu, div_const)
+__device__ __forceinline__ double div_const(double a, double c, double rc) {
+    const double q = a * rc;
+    return fma(fma(-q, c, a), rc, q);
+}
 
 // yy = y + h * sum_j a(S,j) K_j   (j ascending, zero entries skipped at compile time)
 template <int S, int N, int... J>
@@ -261,7 +277,12 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
 #endif
         const double fac11 = detail::pow_eighth(err);
-        const double fac = fmax(kFacc2, fmin(kFacc1, fac11 / kSafe));  // beta = 0
+#if B200CS_LEAN2
+        const double fac11s = detail::div_const(fac11, kSafe, 1.0 / kSafe);
+#else
+        const double fac11s = fac11 / kSafe;
+#endif
+        const double fac = fmax(kFacc2, fmin(kFacc1, fac11s));  // beta = 0
         double hnew = h / fac;
         if (err <= 1.0) {
             // ---- accepted
@@ -323,7 +344,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             reject = false;
         } else {
             // ---- rejected
-            hnew = h / fmin(kFacc1, fac11 / kSafe);
+            hnew = h / fmin(kFacc1, fac11s);
             reject = true;
             last = false;
             ++cnt.rejected;

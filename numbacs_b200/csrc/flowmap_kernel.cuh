@@ -30,13 +30,13 @@ struct KernelShape {
     static constexpr bool kLockstep = false;
 };
 #ifndef B200CS_DG_THREADS
-#define B200CS_DG_THREADS 640
+#define B200CS_DG_THREADS 128
 #endif
 #ifndef B200CS_DG_LOCKSTEP
-#define B200CS_DG_LOCKSTEP true
+#define B200CS_DG_LOCKSTEP false
 #endif
 #ifndef B200CS_DG_MINBLOCKS
-#define B200CS_DG_MINBLOCKS 1
+#define B200CS_DG_MINBLOCKS 5
 #endif
 template <bool DAMPED>
 struct KernelShape<DoubleGyreT<DAMPED>, false> {

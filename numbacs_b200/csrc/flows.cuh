@@ -34,8 +34,8 @@ struct RhsParams {
     double d[4];              // constants derived from p on the host (derive_rhs, capi.cu)
 };
 
-#ifndef B200CS_LEAN
-#define B200CS_LEAN 1
+#ifndef B200CS_LEAN_F
+#define B200CS_LEAN_F 0
 #endif
 #ifndef B200CS_SINPI_WIDE
 #define B200CS_SINPI_WIDE 1
@@ -87,7 +87,7 @@ struct DoubleGyreT {
     __device__ __forceinline__ void eval(double a, double /*t*/, const double (&y)[2], double (&dy)[2]) const {
         const double c = P.d[1];     // p0 * pi*A/2 (exact scalings of pi*A)
         const double b = 1.0 - 2.0 * a;
-#if B200CS_LEAN
+#if B200CS_LEAN_F
         const double f = y[0] * fma(a, y[0], b);         // a*y0**2 + b*y0, one instruction fewer
 #else
         const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
