@@ -115,6 +115,8 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
         R.d[0] = R.p[4] * R.p[0];                                // omega * p0
         R.d[1] = (0.5 * (3.141592653589793 * R.p[1])) * R.p[0];  // p0 * pi * A / 2
         R.d[2] = -(R.p[3] * R.p[0]);                             // -p0 * alpha
+        R.d[3] = R.d[0] / 3.141592653589793;                     // phase of a(t) in half-turns:
+        R.d[4] = R.p[5] / 3.141592653589793;                     //   u = d[3]*t + d[4]
     }
     R.coef_uv = nullptr;
     R.r = f.r;

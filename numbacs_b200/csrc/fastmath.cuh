@@ -212,6 +212,46 @@ __device__ __forceinline__ void sinpi_wide_v(const double (&u)[M], double (&s)[M
     }
 }
 
+// |u| < 2^50 as an integer compare on the high word (false for NaN / inf): the exact reduction
+// k = rint(u), r = u - k of the wide sinpi kernels holds for every such u
+__device__ __forceinline__ bool sinpi_in_range(double u) {
+    return (unsigned)(__double2hiint(u) & 0x7fffffff) < 0x43100000u;
+}
+
+// sin(pi u) in 12 FP64 instructions: the same reduction and polynomial as sinpi_wide_v, with pi
+// folded into the polynomial's constant term, sin(pi r) = r (pi + z Q(z)), instead of the split
+// r pi_hi + r (pi_lo + z Q(z)) -- two instructions fewer per sine.  Measured on 2e7 random
+// arguments (tools/fit_trig_poly.py): max error 2.96 ulp / 3.3e-16 absolute, against 2.33 ulp for
+// the split form and 1.4e-15 absolute for the reference's own sin(pi*x) with |x| < 4, whose
+// argument pi*x is rounded before libm sees it.
+template <int M>
+__device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) {
+    bool slow = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) slow |= !sinpi_in_range(u[m]);
+    if (slow) {  // NaN, inf, or |u| >= 2^50 (every such double is an integer: sin(pi u) = +-0)
+#pragma unroll
+        for (int m = 0; m < M; ++m) s[m] = sincos_slow(3.141592653589793 * u[m]).x;
+        return;
+    }
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = u[m] + kWide.magic;
+        q[m] = __double2loint(t);
+        r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+        z[m] = r[m] * r[m];
+        p[m] = kWide.cp[7];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], kWide.pi_hi), q[m] & 1);
+}
+
 // Branch-free form of sinpi_wide_v.  The reduction above is exact for every |u| < 2^51 (t = u + magic
 // has ulp 1 there), so no libm fall-back is needed below that; NaN and +-inf produce NaN through
 // r = u - k by themselves.  What is left are finite |u| >= 2^51: every such double is a multiple

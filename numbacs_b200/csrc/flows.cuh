@@ -31,14 +31,20 @@ struct RhsParams {
     SplineGridDev grid;       // Spline2D only
     const double2 *coef_uv;   // Spline2D only
     double r;                 // Spline2D spherical radius
-    double d[4];              // constants derived from p on the host (derive_rhs, capi.cu)
+    double d[8];              // constants derived from p on the host (fill_rhs, capi.cu)
 };
 
 #ifndef B200CS_LEAN_F
-#define B200CS_LEAN_F 0
+#define B200CS_LEAN_F 1
 #endif
 #ifndef B200CS_SINPI_WIDE
-#define B200CS_SINPI_WIDE 1
+#define B200CS_SINPI_WIDE 3
+#endif
+#ifndef B200CS_TIME_TURNS
+#define B200CS_TIME_TURNS 1
+#endif
+#ifndef B200CS_SCALED
+#define B200CS_SCALED 1
 #endif
 #ifndef B200CS_SIN_WIDE
 #define B200CS_SIN_WIDE 1
@@ -51,8 +57,12 @@ template <bool DAMPED>
 struct DoubleGyreT {
     static constexpr int N = 2;
     static constexpr int kAux = 1;
+    // the undamped flow leaves the constant amplitudes -c / +c of (dx, dy) to the integrator
+    static constexpr bool kScaled = B200CS_SCALED && !DAMPED;
+    static constexpr bool kAuxAffine = B200CS_TIME_TURNS != 0;
     const RhsParams &P;
     __device__ __forceinline__ explicit DoubleGyreT(const RhsParams &P_) : P(P_) {}
+    __device__ __forceinline__ double scale(int i) const { return i == 0 ? -P.d[1] : P.d[1]; }
 
     // a(t) = eps * sin(omega*tt + psi), tt = p0*t   (flows.py:1152-1153).
     // p[0] is the integration direction, +-1 (userguide.rst:217-227), so folding it into omega
@@ -60,17 +70,41 @@ struct DoubleGyreT {
     // constants are formed once on the host (derive_rhs in capi.cu): P.d[0] = omega*p0,
     // P.d[1] = p0*pi*A/2, P.d[2] = -p0*alpha -- one LDCU each instead of being re-derived from
     // the constant bank in every stage.
+    // With B200CS_TIME_TURNS the phase is kept in half-turns, u = (omega p0/pi) t + psi/pi
+    // (P.d[3], P.d[4] from the host), so that a(t) = eps sin(pi u) uses the exact reduction of the
+    // sinpi kernel (no Cody-Waite steps: one FP64 instruction fewer per stage time); and the
+    // phase at the stage times x + c_s h is affine in c_s, u_s = c_s (wq h) + (wq x + psiq), so
+    // the stage times themselves are never formed.  The phase carries the same kind of rounding
+    // (<= ~1 ulp of the phase) as the reference's omega*tt + psi.
+    template <int M>
+    __device__ __forceinline__ void time_part_affine(double x, double h, const double (&c)[M],
+                                                     double (&aux)[M]) const {
+        const double eps = P.p[2];
+        const double theta = P.d[3] * h, phi = fma(P.d[3], x, P.d[4]);
+        double u[M], sa[M];
+#pragma unroll
+        for (int m = 0; m < M; ++m) u[m] = fma(c[m], theta, phi);
+        sinpi12_v<M>(u, sa);
+#pragma unroll
+        for (int m = 0; m < M; ++m) aux[m] = eps * sa[m];
+    }
+
     template <int M>
     __device__ __forceinline__ void time_part(const double (&t)[M], double (&aux)[M]) const {
-        const double eps = P.p[2], psi = P.p[5];
-        const double omega_p0 = P.d[0];
+        const double eps = P.p[2];
         double arg[M], sa[M];
+#if B200CS_TIME_TURNS
 #pragma unroll
-        for (int m = 0; m < M; ++m) arg[m] = fma(omega_p0, t[m], psi);
+        for (int m = 0; m < M; ++m) arg[m] = fma(P.d[3], t[m], P.d[4]);
+        sinpi12_v<M>(arg, sa);
+#else
+#pragma unroll
+        for (int m = 0; m < M; ++m) arg[m] = fma(P.d[0], t[m], P.p[5]);
 #if B200CS_SIN_WIDE
         sin_wide_v<M>(arg, sa);
 #else
         sin_v<M>(arg, sa);
+#endif
 #endif
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = eps * sa[m];
@@ -99,7 +133,9 @@ struct DoubleGyreT {
         sin_v<2>(arg, s);
 #else
         const double arg[2] = {f + y[1], f - y[1]};
-#if B200CS_SINPI_WIDE == 2
+#if B200CS_SINPI_WIDE == 3
+        sinpi12_v<2>(arg, s);
+#elif B200CS_SINPI_WIDE == 2
         sinpi_wide_nobranch_v<2>(arg, s);
 #elif B200CS_SINPI_WIDE
         sinpi_wide_v<2>(arg, s);
@@ -111,6 +147,9 @@ struct DoubleGyreT {
             const double damp = P.d[2];  // -p0*alpha
             dy[0] = fma(-c, s[0] + s[1], damp * y[0]);
             dy[1] = fma(c * (s[0] - s[1]), df, damp * y[1]);
+        } else if (kScaled) {
+            dy[0] = s[0] + s[1];            // times -c  (scale(0), applied by the integrator)
+            dy[1] = (s[0] - s[1]) * df;     // times +c  (scale(1))
         } else {
             dy[0] = -c * (s[0] + s[1]);
             dy[1] = (c * (s[0] - s[1])) * df;
