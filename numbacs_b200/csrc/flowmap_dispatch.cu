@@ -1,6 +1,5 @@
 // flowmap_dispatch.cu -- flow-kind dispatch of the flow-map kernels + the RHS evaluation kernel.
 #include "common.cuh"
-#include "dop853.cuh"
 #include "flows.cuh"
 #include "launch.cuh"
 
@@ -62,10 +61,7 @@ __global__ void rhs_kernel(const __grid_constant__ RhsParams P, const double *__
     if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(tt, aux);
     rhs.eval(aux[0], tt[0], yy, d);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        if constexpr (rhs_scaled<Rhs>::value) d[i] *= rhs.scale(i);  // the factor the integrator folds into h
-        dy[q * N + i] = d[i];
-    }
+    for (int i = 0; i < N; ++i) dy[q * N + i] = d[i];
 }
 }  // namespace
 

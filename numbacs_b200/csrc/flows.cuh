@@ -43,9 +43,6 @@ struct RhsParams {
 #ifndef B200CS_TIME_TURNS
 #define B200CS_TIME_TURNS 1
 #endif
-#ifndef B200CS_SCALED
-#define B200CS_SCALED 1
-#endif
 #ifndef B200CS_SIN_WIDE
 #define B200CS_SIN_WIDE 1
 #endif
@@ -57,12 +54,9 @@ template <bool DAMPED>
 struct DoubleGyreT {
     static constexpr int N = 2;
     static constexpr int kAux = 1;
-    // the undamped flow leaves the constant amplitudes -c / +c of (dx, dy) to the integrator
-    static constexpr bool kScaled = B200CS_SCALED && !DAMPED;
     static constexpr bool kAuxAffine = B200CS_TIME_TURNS != 0;
     const RhsParams &P;
     __device__ __forceinline__ explicit DoubleGyreT(const RhsParams &P_) : P(P_) {}
-    __device__ __forceinline__ double scale(int i) const { return i == 0 ? -P.d[1] : P.d[1]; }
 
     // a(t) = eps * sin(omega*tt + psi), tt = p0*t   (flows.py:1152-1153).
     // p[0] is the integration direction, +-1 (userguide.rst:217-227), so folding it into omega
@@ -147,9 +141,6 @@ struct DoubleGyreT {
             const double damp = P.d[2];  // -p0*alpha
             dy[0] = fma(-c, s[0] + s[1], damp * y[0]);
             dy[1] = fma(c * (s[0] - s[1]), df, damp * y[1]);
-        } else if (kScaled) {
-            dy[0] = s[0] + s[1];            // times -c  (scale(0), applied by the integrator)
-            dy[1] = (s[0] - s[1]) * df;     // times +c  (scale(1))
         } else {
             dy[0] = -c * (s[0] + s[1]);
             dy[1] = (c * (s[0] - s[1])) * df;
