@@ -15,18 +15,20 @@
 // registers and the tableau's zero entries removed at compile time.
 //
 // What was measured on B200 before settling on this shape (profiles/README.md has the numbers):
-// the kernel is FP64-ISSUE bound -- one DFMA per two cycles per SM sub-partition (8.3-cycle
-// dependent latency), FP64 instructions cannot take constant-bank operands on sm_100, and with
-// ~5 resident warps per sub-partition the dependent chains of one particle are what limits the
-// issue rate.  Variants with 2 or 4 particles per thread and the slopes in shared memory (more
-// ILP, coefficient fetches shared between particles, a single RHS copy in the instruction stream)
-// executed MORE instructions per particle and were 5-40 % slower; an out-of-line RHS removed the
-// instruction-cache stalls of the 62 KB unrolled body but its call overhead cost more (567 vs
-// 598 M points/s).  What did pay: a leaner RHS; batching the time-only part of the RHS over the
-// stage times of a step (known up front), which shortens the dependent chain of every stage; and
-// LOCKSTEP blocks -- one 640-thread block per SM that meets at a barrier every 8 attempts, so its
-// 20 warps walk the unrolled body together and share its instruction-cache footprint (stall on
-// instruction fetch 19 % -> 1 %; a barrier on EVERY attempt gives the gain back as barrier wait).
+// one warp-DFMA issues per two cycles per SM sub-partition (8.3-cycle dependent latency) and FP64
+// instructions cannot take constant-bank operands on sm_100, so the kernel is bound by the FP64
+// pipe AND by the issue slots its non-FP64 instructions take.  Variants with 2 or 4 particles per
+// thread and the slopes in shared memory executed MORE instructions per particle and were
+// 5-40 % slower; an out-of-line RHS cost more in calls than it saved in instruction fetch.
+// What did pay, in order: a leaner RHS (own sine kernels, product-to-sum); batching the time-only
+// part of the RHS over the stage times of a step; and -- for as long as the unrolled attempt loop
+// was larger than the 32 KB L1.5 instruction cache -- LOCKSTEP blocks (one big block per SM that
+// meets at a barrier every 8 attempts, so its warps share the loop's I-cache footprint).  Since
+// round 1c the double-gyre loop is 1600 instructions = 25 KB (single-polynomial sines without
+// parity select, constants folded on the host, damping compiled out): it fits the I-cache, so the
+// double-gyre kernels run as free 128-thread blocks, five per SM (no barrier, no block tail where
+// 8 % of the warp-time idled), FP64 pipe 59 % -> 82 % busy, 664 -> 1014 M points/s at 16384^2.
+// The spline kernels, whose 64-tap RHS makes the loop far larger, keep the lockstep shape.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -163,9 +163,6 @@ __device__ __forceinline__ void sinpi_v(const double (&u)[M], double (&s)[M]) {
 // Coefficients: Chebyshev-node interpolation of (sin(pi r)/r - pi)/r^2 on r^2 in [0, 1/4] and of
 // (sin r / r - 1)/r^2 on [0, (pi/2)^2], computed with 60-digit arithmetic (tools/fit_trig_poly.py);
 // measured error <= 1.5 ulp on 2e5 random arguments.
-#ifndef B200CS_ESTRIN
-#define B200CS_ESTRIN 0
-#endif
 struct __align__(16) WideTrigConsts {
     double magic;        // 1.5 * 2^52
     double pi_hi, pi_lo; // pi = pi_hi + pi_lo
@@ -247,58 +244,19 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
         z[m] = r[m] * r[m];
         p[m] = kWide.cp[7];
     }
-#if B200CS_ESTRIN
-    // Estrin's scheme: dependent depth 4 instead of 7 at the price of two more multiplications
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const double z2 = z[m] * z[m], z4 = z2 * z2;
-        const double a = fma(kWide.cp[1], z[m], kWide.cp[0]), b = fma(kWide.cp[3], z[m], kWide.cp[2]);
-        const double c = fma(kWide.cp[5], z[m], kWide.cp[4]), d = fma(kWide.cp[7], z[m], kWide.cp[6]);
-        p[m] = fma(fma(d, z2, c), z4, fma(b, z2, a));
-    }
-#else
+    // (Estrin's scheme -- depth 4 instead of 7, two more multiplications -- measured slower: 893 vs
+    // 998 M points/s at 8192^2, profiles/r1e_ab_estrin.txt: the FP64 pipe, not the chain, is the limit)
 #pragma unroll
     for (int k = 6; k >= 0; --k)
 #pragma unroll
         for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
-#endif
 #pragma unroll
     for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], kWide.pi_hi), q[m] & 1);
 }
 
-// Branch-free form of sinpi_wide_v.  The reduction above is exact for every |u| < 2^51 (t = u + magic
-// has ulp 1 there), so no libm fall-back is needed below that; NaN and +-inf produce NaN through
-// r = u - k by themselves.  What is left are finite |u| >= 2^51: every such double is a multiple
-// of 1/2 (of 1 from 2^52 on, where sin(pi u) = +-0 exactly) and its own rounding error is a
-// quarter period or more, so the value is meaningless; r is forced to 0 there so that the result
-// is a clean 0 instead of a polynomial evaluated far outside its interval.  Without the branch
-// (and its convergence barrier) a whole step attempt of the double-gyre kernel is one basic
-// block, which lets ptxas start the next stage's a_sj K_j sums under the polynomial chains.
-template <int M>
-__device__ __forceinline__ void sinpi_wide_nobranch_v(const double (&u)[M], double (&s)[M]) {
-    int q[M];
-    double r[M], z[M], p[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const double t = u[m] + kWide.magic;
-        q[m] = __double2loint(t);
-        r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
-        // finite and >= 2^51 (high word in [0x43200000, 0x7ff00000)): unsigned wrap-around compare
-        const unsigned d = (unsigned)(__double2hiint(u[m]) & 0x7fffffff) - 0x43200000u;
-        if (d < 0x3cd00000u) r[m] = 0.0;
-        z[m] = r[m] * r[m];
-        p[m] = kWide.cp[7];
-    }
-#pragma unroll
-    for (int k = 6; k >= 0; --k)
-#pragma unroll
-        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        p[m] = fma(p[m], z[m], kWide.pi_lo);
-        s[m] = flip_sign(fma(r[m], kWide.pi_hi, r[m] * p[m]), q[m] & 1);
-    }
-}
+// (A branch-free form -- no libm fall-back, r forced to 0 for finite |u| >= 2^51 so that a whole step
+// attempt is one basic block -- measured 1-2 % slower than the guarded form: profiles/r1c_ab_variants_a.txt,
+// variants "nb*" / "w2".)
 
 // s[m] = sin(x[m]), wide kernel (|x| < 1e5, else libm)
 template <int M>

@@ -16,13 +16,14 @@ namespace b200cs {
 
 namespace {
 
-// Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow
-// (measured best for the Bickley jet, whose particles need 7-50 attempts: big lockstep blocks wait
-// for their slowest particle).  The spline kernels gain 32 % from lockstep (their 64-tap RHS makes
-// the unrolled body even larger).
-// The final-time double-gyre kernel (the headline workload) runs ONE 640-thread block per SM
-// (20 warps at <= 96 registers) with a block barrier before every step attempt: all 20 warps walk
-// the 62 KB unrolled body together, which removes most of its instruction-cache misses.
+// Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow.
+// The double-gyre kernels (the headline workload) pin that to five blocks per SM (96 registers,
+// no spills): their attempt loop fits the 32 KB L1.5 instruction cache, so free-running small
+// blocks beat every lockstep shape (profiles/r1c_ab_variants_a.txt: 640-thread lockstep 879,
+// 2 x 384 lockstep 907, free 128 x 5 / 192 x 4 / 256 x 3 / 64 x 12 all 915-917 M points/s at 8192^2).
+// The spline kernels gain 32 % from LOCKSTEP -- one 512-thread block per SM whose warps meet at a
+// barrier every 8 attempts and so share the instruction-cache footprint of a loop that is several
+// times the cache (their 64-tap RHS is unrolled into every stage).
 template <class Rhs, bool DENSE>
 struct KernelShape {
     static constexpr int kThreads = 128;

@@ -129,8 +129,6 @@ struct DoubleGyreT {
         const double arg[2] = {f + y[1], f - y[1]};
 #if B200CS_SINPI_WIDE == 3
         sinpi12_v<2>(arg, s);
-#elif B200CS_SINPI_WIDE == 2
-        sinpi_wide_nobranch_v<2>(arg, s);
 #elif B200CS_SINPI_WIDE
         sinpi_wide_v<2>(arg, s);
 #else
