@@ -118,6 +118,7 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
         R.d[3] = R.d[0] / 3.141592653589793;                     // phase of a(t) in half-turns:
         R.d[4] = R.p[5] / 3.141592653589793;                     //   u = d[3]*t + d[4]
     }
+    if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
     R.coef_uv = nullptr;
     R.r = f.r;
     std::memset(&R.grid, 0, sizeof(R.grid));

@@ -169,6 +169,7 @@ struct __align__(16) WideTrigConsts {
     double inv_pi;
     double cp[8];        // sin(pi r) = r pi_hi + r (pi_lo + z (cp0 + z cp1 + ... + z^7 cp7)), z = r^2
     double cs[8];        // sin(r)    = r + r z (cs0 + z cs1 + ... + z^7 cs7)
+    double cc[8];        // cos(r)    = 1 + z (cc0 + z cc1 + ... + z^7 cc7),  |r| <= pi/2
 };
 
 static __constant__ WideTrigConsts kWide = {
@@ -178,7 +179,9 @@ static __constant__ WideTrigConsts kWide = {
     {-5.16771278004997, 2.55016403987734, -0.599264529320343, 0.08214588659675232,
      -0.007370430719634586, 0.00046630087411496363, -2.1906201655131958e-05, 7.725743030789876e-07},
     {-0.16666666666666666, 0.008333333333333316, -0.00019841269841254966, 2.7557319219160833e-06,
-     -2.505210761669045e-08, 1.6058977292642743e-10, -7.643969663988074e-13, 2.7314368769379893e-15}};
+     -2.505210761669045e-08, 1.6058977292642743e-10, -7.643969663988074e-13, 2.7314368769379893e-15},
+    {-0.5, 0.04166666666666634, -0.0013888888888860694, 2.4801587292441663e-05,
+     -2.755731776674132e-07, 2.08766308298722e-09, -1.1464688686901012e-11, 4.6276610380051693e-14}};
 
 // s[m] = sin(pi u[m]), wide kernel
 template <int M>
@@ -286,6 +289,65 @@ __device__ __forceinline__ void sin_wide_v(const double (&x)[M], double (&s)[M])
         for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cs[k]);
 #pragma unroll
     for (int m = 0; m < M; ++m) s[m] = flip_sign(fma(r[m] * z[m], p[m], r[m]), q[m] & 1);
+}
+
+// sin and cos of one argument with the wide kernels: one reduction by pi, two polynomials on
+// |r| <= pi/2, one common sign flip -- 22 FP64 instructions and two LOP3 instead of 20 FP64 plus
+// the parity selects of sincos_fast.  cos is evaluated as 1 + z Pc(z): its ABSOLUTE error is
+// ~2e-16 everywhere, its relative error grows near the zeros of cos (the flows multiply it by an
+// O(1) amplitude and add it to O(1) terms, so absolute accuracy is what matters there).
+__device__ __forceinline__ void sincos_wide(double x, double *s, double *c) {
+    if (!trig_in_range(x)) {
+        const double2 sc = sincos_slow(x);
+        *s = sc.x;
+        *c = sc.y;
+        return;
+    }
+    const double t = fma(x, kWide.inv_pi, kWide.magic);
+    const int q = __double2loint(t);
+    const double k = t - kWide.magic;
+    const double r = fma(-k, kWide.pi_lo, fma(-k, kWide.pi_hi, x));
+    const double z = r * r;
+    double ps = kWide.cs[7], pc = kWide.cc[7];
+#pragma unroll
+    for (int j = 6; j >= 0; --j) {
+        ps = fma(ps, z, kWide.cs[j]);
+        pc = fma(pc, z, kWide.cc[j]);
+    }
+    *s = flip_sign(fma(r * z, ps, r), q & 1);
+    *c = flip_sign(fma(z, pc, 1.0), q & 1);
+}
+
+// expm1(x) for x <= 0 (the Bickley jet's tanh / sech^2 come from em = expm1(-2|Y|)): n = rint(x log2 e),
+// r = x - n ln2 (two FMA steps), expm1(r) = r + r^2 Q(r) with a degree-11 Q on |r| <= ln2 / 2, and
+// e^x - 1 = 2^n expm1(r) + (2^n - 1) in one FMA (exact 2^n - 1: no cancellation for n <= -1, and
+// n = 0 gives expm1(r) itself, so tiny |x| keep full relative accuracy).  The same recipe as CUDA's
+// libm expm1, but with the constants in the constant bank (one LDCU each, kept in uniform
+// registers) instead of 22 UMOV pairs per call site, no branches, and no overflow side: 1.13 ulp
+// on 2e7 arguments in [-64, 0] down to denormals (tests/test_trig_poly_cpu.py).  x below -64 is
+// clamped (e^-64 = 1.6e-28 is far below half an ulp of -1).
+struct __align__(16) Expm1Consts {
+    double log2e, ln2_hi, ln2_lo, pad;
+    double q[12];
+};
+static __constant__ Expm1Consts kExpm1 = {
+    1.4426950408889634, 0.6931471805599453, 2.3190468138462996e-17, 0.0,
+    {0.5, 0.16666666666666666, 0.04166666666666668, 0.008333333333333333, 0.0013888888888879004,
+     0.00019841269841263252, 2.480158733663095e-05, 2.7557319247344507e-06, 2.755726307730941e-07,
+     2.5052070959803662e-08, 2.091821231913398e-09, 1.6086677666787362e-10}};
+
+__device__ __forceinline__ double expm1_neg(double x) {
+    x = fmax(x, -64.0);
+    const double t = fma(x, kExpm1.log2e, kWide.magic);
+    const int n = __double2loint(t);
+    const double k = t - kWide.magic;
+    const double r = fma(-k, kExpm1.ln2_lo, fma(-k, kExpm1.ln2_hi, x));
+    double q = kExpm1.q[11];
+#pragma unroll
+    for (int j = 10; j >= 0; --j) q = fma(q, r, kExpm1.q[j]);
+    const double p = fma(r * r, q, r);
+    const double s = __hiloint2double((n + 1023) << 20, 0);  // 2^n, n in [-93, 0]
+    return fma(p, s, s - 1.0);
 }
 
 __device__ __forceinline__ double sin_fast(double x) {

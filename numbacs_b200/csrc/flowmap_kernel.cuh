@@ -45,6 +45,14 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
     static constexpr int kMinBlocks = B200CS_DG_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_DG_LOCKSTEP;
 };
+#ifdef B200CS_BICKLEY_MINBLOCKS   // A/B only: cap the Bickley kernels' registers through the occupancy hint
+template <bool DENSE>
+struct KernelShape<BickleyJet, DENSE> {
+    static constexpr int kThreads = 128;
+    static constexpr int kMinBlocks = B200CS_BICKLEY_MINBLOCKS;
+    static constexpr bool kLockstep = false;
+};
+#endif
 #ifndef B200CS_SPLINE_THREADS
 #define B200CS_SPLINE_THREADS 512
 #endif

@@ -34,6 +34,9 @@ struct RhsParams {
     double d[8];              // constants derived from p on the host (fill_rhs, capi.cu)
 };
 
+#ifndef B200CS_BICKLEY_WIDE
+#define B200CS_BICKLEY_WIDE 0
+#endif
 #ifndef B200CS_LEAN_F
 #define B200CS_LEAN_F 1
 #endif
@@ -158,19 +161,36 @@ struct BickleyJet {
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
         const double *p = P.p;
         const double tt = p[0] * t;
+#if B200CS_BICKLEY_WIDE
+        // y1 / L_y with the reciprocal from the host and one FMA residual correction: the correctly
+        // rounded quotient in three instructions (the divisor is a launch constant)
+        const double q0 = y[1] * P.d[5];
+        const double Y = fma(fma(-q0, p[2], y[1]), P.d[5], q0);
+#else
         const double Y = y[1] / p[2];
+#endif
         // sech^2(Y) and tanh(Y) from ONE expm1 and one division instead of libm cosh + tanh + a
         // division (the reference's 1/cosh(Y)**2 and tanh(Y), flows.py:1190-1200): with
         // em = expm1(-2|Y|),  tanh|Y| = -em/(2 + em),  sech^2 = 4 (1 + em)/(2 + em)^2; no
         // cancellation anywhere (em is accurate near 0, 2 + em is in [1, 2]).
+#if B200CS_BICKLEY_WIDE
+        const double em = expm1_neg(-2.0 * fabs(Y));
+#else
         const double em = expm1(-2.0 * fabs(Y));
+#endif
         const double inv = 1.0 / (2.0 + em);
         const double th = copysign(-em * inv, Y);
         const double sech2 = (4.0 * (1.0 + em)) * (inv * inv);
         double s1, c1, s2, c2, s3, c3;
+#if B200CS_BICKLEY_WIDE
+        sincos_wide(p[6] * (y[0] - p[9] * tt), &s1, &c1);
+        sincos_wide(p[7] * (y[0] - p[10] * tt), &s2, &c2);
+        sincos_wide(p[8] * (y[0] - p[11] * tt), &s3, &c3);
+#else
         sincos_fast(p[6] * (y[0] - p[9] * tt), &s1, &c1);
         sincos_fast(p[7] * (y[0] - p[10] * tt), &s2, &c2);
         sincos_fast(p[8] * (y[0] - p[11] * tt), &s3, &c3);
+#endif
         const double csum = fma(p[5], c3, fma(p[4], c2, p[3] * c1));
         const double ssum = fma(p[5] * p[8], s3, fma(p[4] * p[7], s2, p[3] * p[6] * s1));
         dy[0] = p[0] * fma(2.0 * p[1] * th * sech2, csum, p[1] * sech2);
