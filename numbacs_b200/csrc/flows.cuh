@@ -35,7 +35,10 @@ struct RhsParams {
 };
 
 #ifndef B200CS_BICKLEY_WIDE
-#define B200CS_BICKLEY_WIDE 0
+#define B200CS_BICKLEY_WIDE 1
+#endif
+#ifndef B200CS_ABC_WIDE
+#define B200CS_ABC_WIDE 1
 #endif
 #ifndef B200CS_LEAN_F
 #define B200CS_LEAN_F 1
@@ -208,9 +211,15 @@ struct Abc {
     __device__ __forceinline__ void time_part(const double (&t)[M], double (&aux)[M]) const {
         const double *p = P.p;
         double arg[M], st[M];
+#if B200CS_ABC_WIDE
+#pragma unroll
+        for (int m = 0; m < M; ++m) arg[m] = p[0] * t[m];
+        sinpi12_v<M>(arg, st);   // sin(pi tt) with the exact reduction (no rounding of pi*tt)
+#else
 #pragma unroll
         for (int m = 0; m < M; ++m) arg[m] = kPi * (p[0] * t[m]);
         sin_v<M>(arg, st);
+#endif
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = fma(p[4] * (p[0] * t[m]), st[m], p[1]);
     }
@@ -218,8 +227,13 @@ struct Abc {
         const double *p = P.p;
         const double arg[2] = {y[0], y[2]};
         double s02[2], s1, c1;
+#if B200CS_ABC_WIDE
+        sin_wide_v<2>(arg, s02);
+        sincos_wide(y[1], &s1, &c1);
+#else
         sin_v<2>(arg, s02);
         sincos_fast(y[1], &s1, &c1);
+#endif
         dy[0] = p[0] * fma(At, s02[1], p[3] * c1);
         dy[1] = p[0] * fma(p[2], s02[0], At * c1);
         // the reference uses y[1] in both terms of dz (flows.py:1258); kept for parity
