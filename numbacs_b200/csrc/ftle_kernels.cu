@@ -61,31 +61,35 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
     // blockIdx.z = frame of a time series: frames are consecutive [nx, ny] grids, one mask for all
     fm += (long long)blockIdx.z * nx * ny;
     out += (long long)blockIdx.z * (row_hi - row_lo) * ny;
-    // everything below the strip origin is 32-bit arithmetic (the launcher checks that a strip of
-    // kRows + 3 rows fits in 2^31 elements); only the three base pointers are 64-bit
     const int rows = (int)((row_hi - i0 < kRows) ? (row_hi - i0) : kRows);
     const int avail = (int)((nx - i0 < kRows + 3) ? (nx - i0) : (kRows + 3));  // rows i0 .. i0+avail-1 exist
-    const int nyi = (int)ny;
-    const bool col_border = (j == 0) || (j == ny - 1);
-    const int offl = (j > 0) ? -1 : 0, offr = (j < ny - 1) ? 1 : 0;
     const int r_first_border = (lo_is_border && i0 == 0) ? 0 : -1;
     const int r_last_border = (hi_is_border && nx - 1 - i0 < kRows) ? (int)(nx - 1 - i0) : -1;
     const double2 zero = make_double2(0.0, 0.0);
-    const double2 *pc = fm + i0 * ny + j;
+    // Four running pointers advanced by one row per iteration (one IMAD.WIDE each); the left /
+    // right neighbours are immediate offsets -16 / +16 bytes from the row pointer.  ncu had this
+    // kernel issue-bound at 127 instructions per pixel, ~30 of them 64-bit address arithmetic
+    // re-derived from (base, 32-bit offset) for every access.
+    const long long stride = ny;
+    const double2 *pc = fm + i0 * ny + j;                 // current row, this column
     const uint8_t *pm = mask ? mask + i0 * ny + j : nullptr;
     double *po = out + (i0 - row_lo) * ny + j;
+    if (j == 0 || j == ny - 1) {                          // border columns: exactly 0, no stencil
+        for (int r = 0; r < rows; ++r, po += stride) *po = 0.0;
+        return;
+    }
     // three live rows in registers plus two rows of read-ahead
-    double2 dn = (i0 >= 1) ? __ldg(pc - nyi) : zero;
+    double2 dn = (i0 >= 1) ? __ldg(pc - stride) : zero;
     double2 mid = __ldg(pc);
-    double2 up = (1 < avail) ? __ldg(pc + nyi) : zero;
-    double2 up2 = (2 < avail) ? __ldg(pc + 2 * nyi) : zero;
-    int o = 0;  // element offset of row i0 + r from the strip origin
+    double2 up = (1 < avail) ? __ldg(pc + stride) : zero;
+    double2 up2 = (2 < avail) ? __ldg(pc + 2 * stride) : zero;
+    const double2 *p3 = pc + 3 * stride;                  // read-ahead row
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
-        const double2 up3 = (r + 3 < avail) ? __ldg(pc + (o + 3 * nyi)) : zero;  // read-ahead
-        const double2 lf = __ldg(pc + (o + offl)), rt = __ldg(pc + (o + offr));
-        bool skip = col_border || r == r_first_border || r == r_last_border;
-        if (pm != nullptr) skip |= (pm[o] != 0);
+        const double2 up3 = (r + 3 < avail) ? __ldg(p3) : zero;
+        const double2 lf = __ldg(pc - 1), rt = __ldg(pc + 1);
+        bool skip = r == r_first_border || r == r_last_border;
+        if (pm != nullptr) skip |= (*pm != 0);
         const double dxdx = (up.x - dn.x) * inv2dx;
         const double dxdy = (rt.x - lf.x) * inv2dy;
         const double dydx = (up.y - dn.y) * inv2dx;
@@ -100,12 +104,15 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
         // max_eig > 1 also filters NaN; huge values (overflowed gradients) go through libm
         if (!skip && max_eig > 1.0)
             val = scaling * (max_eig < 1.0e300 ? log_table(max_eig, tab) : log(max_eig));
-        po[o] = val;
+        *po = val;
         dn = mid;
         mid = up;
         up = up2;
         up2 = up3;
-        o += nyi;
+        pc += stride;
+        p3 += stride;
+        po += stride;
+        if (pm != nullptr) pm += stride;
     }
 }
 
