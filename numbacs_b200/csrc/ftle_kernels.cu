@@ -12,6 +12,12 @@
 //    in registers: every flow-map value is fetched from L2/HBM once per strip (plus one halo row
 //    per kRows); the left / right neighbours come from L1 (the row was just loaded by this block);
 //  * the divisions by 2dx, 2dy are multiplications by reciprocals (<= 1 ulp per derivative);
+//  * addresses are four running pointers advanced one row per iteration with the left / right
+//    neighbours at immediate offsets (round 1g: 127 -> 119 instructions per pixel, 1.43 -> 1.335 ms
+//    at 16384^2 = 73.6 % of the measured HBM copy bandwidth); with that the kernel is no longer
+//    issue bound but memory-latency bound (ncu: long_scoreboard on top, issue slots 62 %, 64
+//    registers -> 8 blocks per SM) -- a variant that saved more instructions at 72 registers and 7
+//    blocks per SM was slower (1.43 ms, profiles/r1h_ftle_16384_rejected_variant.txt);
 //  * log() is a 64-entry table method (top mantissa bits -> 1/c and log c from shared memory,
 //    then a degree-6 log1p on |r| < 2^-7): ~9 FP64 instructions instead of ~30, error ~1e-16.
 #include <cmath>
@@ -31,13 +37,6 @@ struct LogTable {
 };
 __constant__ LogTable kLogTab;
 
-// polynomial / ln 2 constants of log_table in the constant bank: one LDCU each (kept in uniform
-// registers across the unrolled rows) instead of a UMOV pair per use
-struct LogConsts {
-    double c6, c5, c4, c3, ln2;
-};
-__constant__ LogConsts kLogC = {-1.0 / 6.0, 1.0 / 5.0, -1.0 / 4.0, 1.0 / 3.0, 0.6931471805599453};
-
 // natural log of x > 0 (normal, finite) to ~1e-16: x = 2^e * m, m in [1,2)
 __device__ __forceinline__ double log_table(double x, const double2 *__restrict__ tab) {
     const int hi = __double2hiint(x);
@@ -46,18 +45,14 @@ __device__ __forceinline__ double log_table(double x, const double2 *__restrict_
     const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));
     const double2 t = tab[idx];
     const double r = fma(m, t.x, -1.0);  // |r| < 2^-7
-    double p = kLogC.c6;
-    p = fma(p, r, kLogC.c5);
-    p = fma(p, r, kLogC.c4);
-    p = fma(p, r, kLogC.c3);
+    double p = -1.0 / 6.0;
+    p = fma(p, r, 1.0 / 5.0);
+    p = fma(p, r, -1.0 / 4.0);
+    p = fma(p, r, 1.0 / 3.0);
     p = fma(p, r, -0.5);
     p = fma(p, r, 1.0);
-    return fma((double)e, kLogC.ln2, fma(p, r, t.y));
+    return fma((double)e, 0.6931471805599453, fma(p, r, t.y));
 }
-
-// libm log for overflowed gradients (max_eig >= 1e300), out of line: it is never taken on sane
-// data and would otherwise be inlined into each of the four unrolled rows
-__device__ __noinline__ double log_slow(double x) { return log(x); }
 
 __global__ void __launch_bounds__(kCols)
 ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double scaling, double inv2dx,
@@ -114,7 +109,7 @@ ftle_kernel(const double2 *__restrict__ fm, long long nx, long long ny, double s
         double val = 0.0;
         // max_eig > 1 also filters NaN; huge values (overflowed gradients) go through libm
         if (!skip && max_eig > 1.0)
-            val = scaling * (max_eig < 1.0e300 ? log_table(max_eig, tab) : log_slow(max_eig));
+            val = scaling * (max_eig < 1.0e300 ? log_table(max_eig, tab) : log(max_eig));
         *po = val;
         dn = mid;
         mid = up;
