@@ -71,9 +71,11 @@ namespace detail {
 // err^(1/8) with three correctly rounded square roots (libm pow in the reference; the difference
 // is <= 1 ulp and only scales the next step size)
 #if B200CS_LEAN2
-// three square roots as x * rsqrt(x) (MUFU seed + one Newton step each, <= 2 ulp; x > 0 here or the
-// result is only compared / clamped) instead of three correctly rounded ones
-__device__ __forceinline__ double sqrt_fast(double x) { return x > 0.0 ? x * rsqrt(x) : 0.0; }
+// three square roots as x * rsqrt(x) (MUFU seed + one Newton step each, <= 2 ulp) instead of three
+// correctly rounded ones.  NaN must stay NaN (a NaN error norm has to reach the controller's
+// fmin / fmax as NaN so that the step is rejected with h/3, ending in B200CS_ST_HSMALL after a
+// few dozen attempts, exactly as with sqrt); +inf gives NaN, which the same fmin treats like +inf.
+__device__ __forceinline__ double sqrt_fast(double x) { return x == 0.0 ? 0.0 : x * rsqrt(x); }
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt_fast(sqrt_fast(sqrt_fast(x))); }
 #else
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
