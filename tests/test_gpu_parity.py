@@ -506,6 +506,28 @@ def test_empty_and_degenerate_inputs(nb):
     assert ft.shape == (131, 67) and not ft[0].any() and not ft[:, -1].any() and ft[1:-1, 1:-1].any()
 
 
+def test_nan_particles_terminate_and_do_not_disturb_their_neighbours(nb):
+    """A NaN initial condition must end with a non-OK status after a bounded number of rejected
+    attempts (the NaN error norm rejects with h/3 until the step size is below round-off, as in
+    Hairer's code) and must not change any other particle of the launch."""
+    import time
+    pts = np.random.default_rng(5).uniform((0, 0), (2, 1), size=(4096, 2))
+    bad = pts.copy()
+    bad[[7, 1000, 4095], 0] = np.nan
+    bad[2048, 1] = np.nan
+    isbad = np.isnan(bad).any(axis=1)
+    for name in ("double_gyre", "bickley_jet"):
+        f, p, _ = nb.flows.get_predefined_flow(name)
+        ref = nb.integration.flowmap(f, 0.5, 4.0, pts, p)
+        info = {}
+        t0 = time.perf_counter()
+        out = nb.integration.flowmap(f, 0.5, 4.0, bad, p, info=info)
+        assert time.perf_counter() - t0 < 20.0
+        assert (info["status"][isbad] != 1).all() and (info["status"][~isbad] == 1).all()
+        assert np.isnan(out[isbad]).any(axis=1).all()
+        assert np.array_equal(out[~isbad], ref[~isbad])
+
+
 def test_torch_tensors_stay_on_device(nb):
     torch = pytest.importorskip("torch")
     f, p, _ = nb.flows.get_predefined_flow("double_gyre", int_direction=-1.0)
