@@ -1,15 +1,25 @@
-// fastmath.cuh -- lean FP64 sin / cos for the right-hand sides.
+// fastmath.cuh -- lean FP64 sin / cos / expm1 for the right-hand sides.
 //
-// The RHS of the analytic flows is dominated by sin/cos (flows.py:1152-1158: five per call).
-// CUDA's libm versions are accurate but wrap ~24 FP64 instructions in ~60 integer / uniform /
-// branch instructions (immediates materialised with UMOV pairs, inf/NaN checks, a Payne-Hanek
-// slow path behind a CALL).  On B200 the FP64 pipe issues one warp instruction every two cycles
-// per SM sub-partition and an FP64 instruction cannot take a constant-bank operand directly, so
-// that overhead -- not FP64 throughput -- would bound the kernel.  These versions keep the same
-// numerical recipe (3-term Cody-Waite reduction by pi/2 with FMA, the classical minimax kernels
-// on [-pi/4, pi/4], error < 1 ulp) with a branch-free quadrant fix-up, and evaluate M independent
-// arguments side by side (M dependency chains, each constant fetched once).  Arguments with
-// |x| >= 1e5 (never produced by the flows' own domains) fall back to libm, out of line.
+// The RHS of the analytic flows is dominated by transcendentals (flows.py:1152-1158: five sin/cos
+// per double-gyre call; flows.py:1189-1213: cosh, tanh and six sin/cos per Bickley call).  CUDA's
+// libm versions are accurate but wrap ~24 FP64 instructions in ~60 integer / uniform / branch
+// instructions (immediates materialised with UMOV pairs, inf/NaN checks, a Payne-Hanek slow path
+// behind a CALL).  On B200 the FP64 pipe issues one warp instruction every two cycles per SM
+// sub-partition and an FP64 instruction cannot take a constant-bank operand directly, so that
+// overhead -- not FP64 throughput -- would bound the kernels.  Two families live here:
+//   * the "wide" kernels (sinpi12_v, sin_wide_v, sincos_wide, expm1_neg; round 1c-1f): reduce to
+//     half a period only and evaluate ONE odd / even polynomial there, so a sine is 12-14 FP64
+//     instructions plus a sign flip and every coefficient is a warp-uniform constant-bank load.
+//     These are what the double-gyre, Bickley-jet and ABC right-hand sides use;
+//   * the parity-selected kernels (sin_v, sinpi_v, sincos_fast; rounds 1a/1b): reduce to a
+//     quarter period with the classical minimax kernels on [-pi/4, pi/4] (< 1 ulp) and pick the
+//     sine or cosine polynomial per lane through an indexed constant load.  One FP64 instruction
+//     fewer per sine but ~15 more issue slots; still used by cos_fast (one call per spline RHS)
+//     and kept for A/B builds (B200CS_SINPI_WIDE=0 etc., tools/build_variant.py).
+// All of them evaluate M independent arguments side by side (M dependency chains, each constant
+// fetched once) and hand arguments outside their exact-reduction range (|x| >= 1e5, for sin(pi u)
+// |u| >= 2^50, NaN, inf) to libm, out of line.  Accuracy is measured on the CPU from the constants
+// in this file (tests/test_trig_poly_cpu.py, tools/fit_trig_poly.py).
 #pragma once
 #include <cuda_runtime.h>
 
