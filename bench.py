@@ -24,7 +24,13 @@ A step = one full flow map + FTLE pass.
   ridge_tail    : config 5's "+ FTLE ridge extraction" (C_eig_2D -> ftle_from_eig -> ftle_ridge_pts on
           the step's flow map), timed on its own after the K steps and reported beside the metric.
   cpu_baseline  : the CPU oracle (a port of the reference algorithm, oracle/) on all host threads
-          over a bounded contiguous row sample of the same grid.
+          over a bounded contiguous row sample of the same grid (best of 3).
+  parity        : the oracle's rows of that sample against the GPU's rows of the SAME 16384^2 grid
+          (SURVEY section 8d "Parity gates"): step-count mismatches, max|dx|/L over step-matching
+          particles and over all, FTLE relative L2 with the stencils touching a mismatch left out.
+          At N > 1 the sample straddles the cut between rank 0's and rank 1's row blocks.
+  gather_ms     : the final gather -- every rank's FTLE block into the assembled field on rank 0
+          (sharded.gather_rows: one irecv per peer straight into the destination rows).
 
 --impl reference times the reference's CPU implementation of the path.  The reference is pure
 Python + numba whose solver / spline live in third-party packages that are not installed and
@@ -55,30 +61,47 @@ def workload_name(n):
 
 # ------------------------------------------------------------------ reference arm / CPU baseline
 
-def cpu_sample(n, rows, reps=1):
-    """Oracle flow map + FTLE on `rows` contiguous rows (plus one halo row each side) of the
-    n x n grid, all host threads.  Returns (points per second, seconds per rep, threads)."""
+def host_threads():
+    """All host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the
+    CPU arm must not inherit that, so the oracle's thread count is set explicitly."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_sample(n, rows, reps=1, i0=None, keep=False):
+    """Oracle flow map + FTLE on `rows` contiguous rows [i0, i0 + rows) of the n x n grid, all host
+    threads, best of `reps`.  Returns a dict: points per second, seconds, threads and (keep=True)
+    the flow map, per-particle step counts and FTLE rows for the parity block."""
     import oracle as O
     O.build()
+    O.set_num_threads(host_threads())
     f, p, _ = O.get_predefined_flow("double_gyre", int_direction=-1.0)
     x, y = np.linspace(0, 2, n), np.linspace(0, 1, n)
-    i0 = n // 4
-    xs = x[i0 - 1:i0 + rows + 1]
+    if i0 is None:
+        i0 = n // 4
+    xs = x[i0:i0 + rows]
     best = float("inf")
     for _ in range(reps):
         t = time.perf_counter()
-        fm = O.flowmap_grid_2D(f, T0, TINT, xs, y, p, rtol=RTOL, atol=ATOL)
-        O.ftle_grid_2D(fm, TINT, x[1] - x[0], y[1] - y[0])
+        fm, _, _, steps, _ = O.flowmap_grid_2D(f, T0, TINT, xs, y, p, rtol=RTOL, atol=ATOL, full=True)
+        ft = O.ftle_grid_2D(fm, TINT, x[1] - x[0], y[1] - y[0])
         best = min(best, time.perf_counter() - t)
-    # the two halo rows are integrated too; count them as work done
-    return (rows + 2) * n / best, best, O.num_threads()
+    out = {"pps": rows * n / best, "seconds": best, "threads": O.num_threads(), "rows": rows, "i0": i0}
+    if keep:
+        out.update(fm=fm, steps=steps, ftle=ft)
+    return out
 
 
 def pick_rows(n, target_s):
-    """Rows of the n x n grid the oracle integrates in about target_s seconds."""
-    pps, _, _ = cpu_sample(n, 6)
-    rows = int(pps * target_s / n)
-    return max(8, min(rows, n - 2))
+    """Rows of the n x n grid the oracle integrates in about target_s seconds (a multiple of 8)."""
+    pps = cpu_sample(n, 8)["pps"]
+    rows = int(pps * target_s / n) // 8 * 8
+    return max(8, min(rows, n))
+
+
+CPU_TARGET_S = 4.0   # seconds per repetition of the CPU sample, both arms (best of 3 -> ~12 s)
 
 
 def run_reference(args):
@@ -86,16 +109,18 @@ def run_reference(args):
     if rank != 0:
         return  # one CPU run per node; the other ranks exit without work
     n = args.n
-    rows = args.cpu_rows or pick_rows(n, 6.0)
+    rows = args.cpu_rows or pick_rows(n, CPU_TARGET_S)
     for _ in range(args.warmup):
         cpu_sample(n, max(8, rows // 8))
     times = []
     for _ in range(args.steps):
-        _, t, threads = cpu_sample(n, rows)
-        times.append(t)
+        r = cpu_sample(n, rows)
+        times.append(r["seconds"])
+    threads = r["threads"]
     t_step = float(np.mean(times))
-    val = (rows + 2) * n / t_step
-    sample = f"{rows + 2} contiguous rows x {n} columns of the {n}x{n} grid per step ({(rows + 2) * n} particles)"
+    t_best = float(np.min(times))
+    val = rows * n / t_step
+    sample = f"{rows} contiguous rows x {n} columns of the {n}x{n} grid per step ({rows * n} particles)"
     line = {
         "impl": "reference", "metric": "FTLE grid points/s (flowmap+FTLE)", "value": val,
         "unit": "grid points/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -103,9 +128,10 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(n), "sample": sample},
         "cpu_baseline": {"value": val, "unit": "grid points/s", "cores": threads, "kind": "port",
-                         "sample": sample,
-                         "note": "oracle/ C restatement of the reference algorithm (OpenMP over particles); "
-                                 "the reference's own numba path cannot run: numbalsoda / interpolation "
+                         "sample": sample, "best_of_steps_value": rows * n / t_best,
+                         "note": "oracle/ C restatement of the reference algorithm (OpenMP over particles, "
+                                 "thread count set explicitly to every host core this process may use); the "
+                                 "reference's own numba path cannot run: numbalsoda / interpolation "
                                  "are not installed and there is no network"},
         "e2e": {"value": val, "unit": "grid points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "host_cpus": os.cpu_count(),
@@ -166,13 +192,34 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ the B200 arm
 
+def shared_pinned(name, count, create):
+    """A float64 host buffer of `count` elements that every rank of the node maps (POSIX shared
+    memory) and registers with CUDA, so each GPU downloads its rows of the assembled result
+    straight into its slice -- the final gather to host memory uses all PCIe links at once and
+    rank 0 ends up holding the whole field.  Returns (tensor, path) or (None, None)."""
+    import torch
+    path = f"/dev/shm/{name}"
+    try:
+        if create:
+            with open(path, "wb") as fh:
+                fh.truncate(count * 8)
+        t = torch.from_file(path, shared=True, size=count, dtype=torch.float64)
+        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), count * 8, 0)
+        if int(rc) != 0:
+            return None, path
+        return t, path
+    except Exception:
+        return None, path
+
+
 def run_b200(args):
     import ctypes as C
     import torch
     import torch.distributed as dist
     from numbacs_b200 import _build, _lib
     from numbacs_b200.flows import get_predefined_flow
-    from numbacs_b200.sharded import balanced_row_blocks, estimate_row_cost, exchange_halo_rows
+    from numbacs_b200.sharded import (balanced_row_blocks, estimate_row_cost, exchange_halo_rows,
+                                      gather_rows, gather_points)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -195,28 +242,39 @@ def run_b200(args):
     n = args.n
     K, W = args.steps, args.warmup
     dx, dy = 2.0 / (n - 1), 1.0 / (n - 1)
+    HW = 2 if world > 1 else 0     # halo rows per interior edge: 2 (the ridge tail reads i +- 2; FTLE needs 1)
     f, params, _ = get_predefined_flow("double_gyre", int_direction=-1.0)
+    x_host = torch.linspace(0, 2, n, dtype=torch.float64).pin_memory()
+    y_host = torch.linspace(0, 1, n, dtype=torch.float64).pin_memory()
+    x_dev, y_dev = x_host.cuda(), y_host.cuda()
+
     # row blocks of equal estimated COST (step attempts), not equal size: a 256 x 256 subsample of
-    # the grid is integrated once (planning, outside the timed steps; every rank gets the same cuts)
-    t_plan = time.perf_counter()
-    if world > 1:
-        cost = estimate_row_cost(f, T0, TINT, np.linspace(0, 2, n), np.linspace(0, 1, n), params, RTOL, ATOL)
-        blocks = balanced_row_blocks(cost, world)
-    else:
-        blocks = [(0, n)]
-    t_plan = time.perf_counter() - t_plan
+    # the grid is integrated on the device and reduced per row there (every rank gets the same cuts)
+    def plan():
+        if world == 1:
+            return [(0, n)]
+        cost = estimate_row_cost(f, T0, TINT, x_dev, y_dev, params, RTOL, ATOL)
+        return balanced_row_blocks(cost, world, min_rows=HW)
+
+    plan()
+    torch.cuda.synchronize()
+    t_plan = []
+    for _ in range(5):
+        t = time.perf_counter()
+        blocks = plan()
+        torch.cuda.synchronize()
+        t_plan.append(time.perf_counter() - t)
+    plan_ms = float(np.median(t_plan)) * 1e3
     i0, i1 = blocks[rank]
     rows = i1 - i0
     has_lo, has_hi = int(rank > 0), int(rank < world - 1)
 
-    x_host = torch.linspace(0, 2, n, dtype=torch.float64).pin_memory()
-    y_host = torch.linspace(0, 1, n, dtype=torch.float64).pin_memory()
-    x_dev, y_dev = x_host.cuda(), y_host.cuda()
     x_rows_dev = x_dev[i0:i1].contiguous()
-    slab = torch.empty((has_lo + rows + has_hi, n, 2), dtype=torch.float64, device="cuda")
-    own = slab[has_lo:has_lo + rows]
+    slab = torch.empty((HW * has_lo + rows + HW * has_hi, n, 2), dtype=torch.float64, device="cuda")
+    own = slab[HW * has_lo:HW * has_lo + rows]
+    # the FTLE kernel sees the slab with ONE halo row per interior edge
+    ftle_view = slab[(HW - 1) * has_lo:slab.shape[0] - (HW - 1) * has_hi]
     ftle = torch.empty((rows, n), dtype=torch.float64, device="cuda")
-    ftle_host = torch.empty((rows, n), dtype=torch.float64).pin_memory()
     stats = torch.zeros(3, dtype=torch.int64, device="cuda")
     p_arr = np.ascontiguousarray(params)
     stream = torch.cuda.current_stream()
@@ -230,13 +288,16 @@ def run_b200(args):
             C.c_void_p(stats.data_ptr()) if with_stats else None, sptr))
 
     def k_ftle():
-        _lib.check(L.b200cs_ftle_slab_2d(C.c_void_p(slab.data_ptr()), slab.shape[0], n, TINT, dx, dy,
+        _lib.check(L.b200cs_ftle_slab_2d(C.c_void_p(ftle_view.data_ptr()), ftle_view.shape[0], n, TINT, dx, dy,
                                          None, has_lo, has_hi, C.c_void_p(ftle.data_ptr()), sptr))
+
+    def halo():
+        if world > 1:
+            exchange_halo_rows(slab, has_lo, has_hi, rank, width=HW)
 
     def step(xr, yv, with_stats=False):
         k_flowmap(xr, yv, with_stats)
-        if world > 1:
-            exchange_halo_rows(slab, has_lo, has_hi, rank)
+        halo()
         k_ftle()
 
     def sync_all():
@@ -264,8 +325,7 @@ def run_b200(args):
         ev[k][0].record(stream)
         k_flowmap(x_rows_dev, y_dev, False)
         ev[k][1].record(stream)
-        if world > 1:
-            exchange_halo_rows(slab, has_lo, has_hi, rank)
+        halo()
         ev[k][2].record(stream)
         k_ftle()
         ev[k][3].record(stream)
@@ -280,44 +340,134 @@ def run_b200(args):
         dist.barrier()
     clocks = sampler.stop() if sampler else None
 
-    # ---- end-to-end region: ONE C-ABI call per step with HOST buffers only -- x / y slab in from
-    # pinned memory, the FTLE block out to pinned memory (b200cs_flowmap_ftle_grid_2d integrates in
-    # row chunks and streams finished FTLE rows over PCIe while the next chunk is integrated).
-    # Multi-GPU: every rank passes its row block plus one stencil-only halo row per interior edge
-    # (recomputed, 2 of nx/N rows), so the end-to-end path needs no exchange at all.
-    xs_host = x_host[i0 - has_lo:i1 + has_hi]
-    def e2e_step():
-        _lib.check(L.b200cs_flowmap_ftle_grid_2d(
-            f, T0, TINT, C.c_void_p(xs_host.data_ptr()), xs_host.shape[0], C.c_void_p(y_host.data_ptr()), n,
-            C.c_void_p(p_arr.ctypes.data), len(p_arr), 0, RTOL, ATOL, None, dx, dy, has_lo, has_hi,
-            None, C.c_void_p(ftle_host.data_ptr()), None, None, sptr))
+    # ---- the final gather over NVLink: every rank's FTLE block into the assembled field on rank 0
+    gather_ms = 0.0
+    if world > 1:
+        full_ftle = torch.empty((n, n), dtype=torch.float64, device="cuda") if rank == 0 else None
+        gather_rows(ftle, n, blocks=blocks, out=full_ftle)       # warm-up (NCCL connections)
+        sync_all()
+        best = float("inf")
+        for _ in range(3):
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            gather_rows(ftle, n, blocks=blocks, out=full_ftle)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, g0.elapsed_time(g1))
+            dist.barrier()
+        gather_ms = best
+        gathered_checksum = float(full_ftle.sum()) if rank == 0 else 0.0
+        del full_ftle
+        torch.cuda.empty_cache()
 
-    e2e_step()
+    # ---- end-to-end region: per step, every rank re-plans its row block (the 256 x 256 cost
+    # estimate, on the device) and makes ONE C-ABI call with HOST buffers only -- x / y in from
+    # pinned memory, its FLOW-MAP rows and its FTLE rows out to host memory
+    # (b200cs_flowmap_ftle_grid_2d integrates in row chunks and streams finished rows over PCIe
+    # while the next chunk is integrated).  The host destination is ONE buffer per field shared by
+    # all ranks of the node (POSIX shared memory, registered with CUDA in every process): each GPU
+    # writes its rows into its slice over its own PCIe link, so when the step ends rank 0 holds the
+    # assembled [n, n, 2] flow map and [n, n] FTLE field -- what the reference's flowmap_grid_2D +
+    # ftle_grid_2D return -- without any device-side gather.  Multi-GPU: every rank passes its row
+    # block plus one stencil-only halo row per interior edge (recomputed, 2 of nx/N rows), so the
+    # end-to-end path needs no exchange at all.
+    tag = f"b200cs_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, rank == 0) if world == 1 else (None, None)
+    fm_sh, fm_path = (None, None)
+    if world > 1:
+        if rank == 0:
+            ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, True)
+            fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, True)
+        dist.barrier()
+        if rank != 0:
+            ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, False)
+            fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, False)
+        ok = torch.tensor([int(ft_sh is not None and fm_sh is not None)], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        assembled = bool(int(ok))
+    else:
+        fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, True)
+        assembled = ft_sh is not None and fm_sh is not None
+    if not assembled:   # no shared memory: every rank keeps its rows in its own pinned buffer
+        ft_sh = torch.empty(n * n if world == 1 else rows * n, dtype=torch.float64).pin_memory()
+        fm_sh = torch.empty(2 * (n * n if world == 1 else rows * n), dtype=torch.float64).pin_memory()
+    ft_full = ft_sh.view(-1, n)
+    fm_full = fm_sh.view(-1, n, 2)
+
+    def e2e_step():
+        b = plan()
+        a0, a1 = b[rank]
+        r0 = a0 if assembled or world == 1 else 0
+        xs = x_host[a0 - has_lo:a1 + has_hi]
+        _lib.check(L.b200cs_flowmap_ftle_grid_2d(
+            f, T0, TINT, C.c_void_p(xs.data_ptr()), xs.shape[0], C.c_void_p(y_host.data_ptr()), n,
+            C.c_void_p(p_arr.ctypes.data), len(p_arr), 0, RTOL, ATOL, None, dx, dy, has_lo, has_hi,
+            None, C.c_void_p(ft_full[r0:].data_ptr()), None, None, sptr))
+        return a0, a1
+
+    def e2e_step_fm():
+        # the same call, the flow-map rows downloaded as well (halo rows land in a scratch slab:
+        # the C entry writes flowmap_out for every row it integrates)
+        b = plan()
+        a0, a1 = b[rank]
+        r0 = a0 if assembled or world == 1 else 0
+        xs = x_host[a0 - has_lo:a1 + has_hi]
+        dst = fm_full[r0 - has_lo:] if (assembled and world > 1) else fm_full
+        _lib.check(L.b200cs_flowmap_ftle_grid_2d(
+            f, T0, TINT, C.c_void_p(xs.data_ptr()), xs.shape[0], C.c_void_p(y_host.data_ptr()), n,
+            C.c_void_p(p_arr.ctypes.data), len(p_arr), 0, RTOL, ATOL, None, dx, dy, has_lo, has_hi,
+            C.c_void_p(dst.data_ptr()), C.c_void_p(ft_full[r0:].data_ptr()), None, None, sptr))
+
+    def timed_e2e(fn):
+        fn()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            dist.barrier()
+        return ms
+
+    e2e_ms = timed_e2e(e2e_step)
+    # halo rows of neighbouring ranks overlap by one row in the shared flow-map buffer (both write
+    # the same values), so the with-flow-map variant is only run when that is well defined
+    e2e_fm_ms = timed_e2e(e2e_step_fm) if (world == 1 or assembled) else None
     sync_all()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        e2e_step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1)
-    checksum = float(ftle_host.sum()) if rows else 0.0   # device->host result actually read
+    if assembled or world == 1:
+        checksum = float(ft_full.sum()) if rank == 0 else 0.0   # the assembled host field, read on rank 0
+    else:
+        checksum = float(ft_full[:rows].sum())
+
+    # ---- parity block: oracle rows vs the GPU's rows of the same grid
+    parity = None
+    cpu = None
+    if not args.no_cpu:
+        parity, cpu = parity_block(args, n, world, rank, blocks, slab, own, ftle, HW, has_lo, f, params,
+                                   x_dev, y_dev, dx, dy)
 
     # ---- config 5's tail, reported beside the metric (not inside it): Cauchy-Green eigen-pairs ->
     # FTLE from the largest eigenvalue -> sub-pixel ridge points, on the flow map of the last step
-    # (examples/ftle/plot_dg_ftle_ridges.py:43-72: percentile 0, sdd_thresh 10).  N = 1 only.
+    # (examples/ftle/plot_dg_ftle_ridges.py:43-72: percentile 0, sdd_thresh 10).  At N > 1 every
+    # rank runs the tail on its slab (two-row halo, sharded.flowmap_ridges_sharded's scheme) and
+    # the ridge points are gathered on rank 0.
     ridge = None
-    if world == 1 and not args.no_ridges:
+    if not args.no_ridges:
         from numbacs_b200.diagnostics import C_eig_2D, ftle_from_eig
         from numbacs_b200.extraction import ftle_ridge_pts
-        fm_full = slab[has_lo:has_lo + rows]
+        x_slab = x_dev[i0 - HW * has_lo:i1 + HW * has_hi]
 
         def tail():
-            vals, vecs = C_eig_2D(fm_full, dx, dy)
+            vals, vecs = C_eig_2D(slab, dx, dy)
             ft2 = ftle_from_eig(vals[:, :, 1], TINT)
-            return ft2, ftle_ridge_pts(ft2, vecs[:, :, :, 1], x_dev, y_dev, sdd_thresh=10.0, percentile=0)
+            return ft2, ftle_ridge_pts(ft2, vecs[:, :, :, 1], x_slab, y_dev, sdd_thresh=10.0, percentile=0,
+                                       spacing=(dx, dy))
 
         tail()
+        sync_all()
         best = float("inf")
         for _ in range(3):
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -326,23 +476,59 @@ def run_b200(args):
             r1.record(stream)
             torch.cuda.synchronize()
             best = min(best, r0.elapsed_time(r1))
-        ridge = {"ms": best, "n_ridge_pts": int(rp.shape[0]),
-                 "ftle_vs_ftle_grid_2D_rel_l2": float(torch.linalg.norm(ft2 - ftle) / torch.linalg.norm(ftle)),
+        ft2_own = ft2[HW * has_lo:HW * has_lo + rows]
+        num = float(torch.linalg.norm(ft2_own - ftle) ** 2)
+        den = float(torch.linalg.norm(ftle) ** 2)
+        tt = torch.tensor([best, float(rp.shape[0]), num, den], dtype=torch.float64, device="cuda")
+        g_ms = 0.0
+        if world > 1:
+            mx = tt.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+            best = float(mx[0])
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            allp = gather_points(rp, dst=0)
+            g1.record(stream)
+            torch.cuda.synchronize()
+            g_ms = g0.elapsed_time(g1)
+            del allp
+        ridge = {"ms": best, "n_ridge_pts": int(tt[1]),
+                 "ftle_vs_ftle_grid_2D_rel_l2": float(np.sqrt(float(tt[2]) / float(tt[3]))),
+                 "gather_points_ms": g_ms,
                  "kernels": "C_eig_2D + ftle_from_eig + ftle_ridge_pts (detect, scan, compact), device-timed, "
-                            "best of 3; sdd_thresh=10, percentile=0",
+                            "best of 3, max over ranks; sdd_thresh=10, percentile=0",
                  "algorithmic_bytes_per_point": 64 + 16 + 2 * 24}
         del ft2, rp
         torch.cuda.empty_cache()
 
     # ---- max over ranks
-    t = torch.tensor([span_ms, e2e_ms, fm_ms, ft_ms, halo_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([span_ms, e2e_ms, fm_ms, ft_ms, halo_ms, gather_ms, plan_ms,
+                      e2e_fm_ms if e2e_fm_ms is not None else 0.0], dtype=torch.float64, device="cuda")
     agg = torch.cat([torch.tensor(st, dtype=torch.float64, device="cuda"),
                      torch.tensor([checksum], dtype=torch.float64, device="cuda")])
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-    span_ms, e2e_ms, fm_ms, ft_ms, halo_ms = t.tolist()
+    span_ms, e2e_ms, fm_ms, ft_ms, halo_ms, gather_ms, plan_ms, e2e_fm_max = t.tolist()
     nfev, nacc, nrej, checksum = agg.tolist()
+    if e2e_fm_ms is not None:
+        e2e_fm_ms = e2e_fm_max
+
+    # release the shared host buffers
+    try:
+        if assembled:
+            torch.cuda.cudart().cudaHostUnregister(ft_sh.data_ptr())
+            torch.cuda.cudart().cudaHostUnregister(fm_sh.data_ptr())
+        del ft_full, fm_full, ft_sh, fm_sh
+        if world > 1:
+            dist.barrier()
+        if rank == 0:
+            for pth in (ft_path, fm_path):
+                if pth and os.path.exists(pth):
+                    os.unlink(pth)
+    except Exception:
+        pass
 
     if rank == 0:
         pts = float(n) * n
@@ -368,15 +554,6 @@ def run_b200(args):
         except Exception:
             ftle_traffic = None
         ftle_gbs = 24.0 * pts / world / (ft_ms * 1e-3) / 1e9
-        # bounded CPU sample of the same workload on this box's host cores (rank 0, N = 1 only)
-        cpu = None
-        if world == 1 and not args.no_cpu:
-            rows_cpu = args.cpu_rows or pick_rows(n, 12.0)
-            v, tsec, threads = cpu_sample(n, rows_cpu)
-            cpu = {"value": v, "unit": "grid points/s", "cores": threads, "kind": "port",
-                   "sample": f"{rows_cpu + 2} contiguous rows x {n} columns of the same grid "
-                             f"({(rows_cpu + 2) * n} particles, {tsec:.1f} s), oracle/ C port with OpenMP",
-                   "host_cpus": os.cpu_count()}
         line = {
             "metric": "FTLE grid points/s (flowmap+FTLE)", "value": value, "unit": "grid points/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -384,16 +561,27 @@ def run_b200(args):
             "data": "synthetic",
             "config": {"workload": workload_name(n),
                        "parallelism": f"row-block x{world}" + (", blocks balanced by estimated step count "
-                                                              f"(planning {t_plan * 1e3:.1f} ms, not timed)" if world > 1 else ""),
+                                                              f"(planning {plan_ms:.2f} ms per call: outside the "
+                                                              "device-timed steps, INSIDE every end-to-end step)"
+                                                              if world > 1 else ""),
                        "row_blocks": [list(b) for b in blocks],
                        "l2": "no flush: every step rewrites 24 B/point of outputs "
                              f"({24 * pts / world / 1e9:.2f} GB per GPU >> 126 MB L2), inputs are 2 x {n} doubles"},
             "e2e": {"value": e2e_val, "unit": "grid points/s",
                     "h2d_bytes_per_step": int(8 * (n + 2 * (world - 1) + n * world)),
                     "d2h_bytes_per_step": int(8 * pts), "ms_per_step": e2e_ms / K,
+                    "assembled_on_rank0_host": bool(assembled or world == 1),
+                    "planning_inside": world > 1,
                     "result": "one b200cs_flowmap_ftle_grid_2d call per rank and step, host pointers only: x/y "
-                              "from pinned memory, FTLE field to pinned memory (downloads overlap the "
-                              "integration of later row chunks); the flow map stays in HBM"},
+                              "from pinned memory, FTLE rows into ONE host buffer shared by all ranks (POSIX "
+                              "shared memory registered with CUDA in every process), so rank 0 holds the "
+                              "assembled field when the step ends; downloads overlap the integration of later "
+                              "row chunks; the per-step planning pass (cost-balanced cuts) is inside",
+                    "with_flowmap": None if e2e_fm_ms is None else {
+                        "value": pts / (e2e_fm_ms / K * 1e-3), "ms_per_step": e2e_fm_ms / K,
+                        "d2h_bytes_per_step": int(24 * pts),
+                        "note": "the same call with flowmap_out set: the [n, n, 2] flow map that the reference's "
+                                "flowmap_grid_2D returns is downloaded too (16 B/point more over PCIe)"}},
             "gpu_launches": 2 * K * world,  # timed (device) region: flow-map + FTLE kernel per step and rank
             "roofline": {"bound": "fp64", "achieved": fm_tflops_per_gpu, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": fm_tflops_per_gpu / fp64_peak, "traffic": traffic,
@@ -407,14 +595,24 @@ def run_b200(args):
             "roofline_ftle": {"bound": "hbm", "achieved": ftle_gbs, "peak": hbm_peak, "unit": "GB/s",
                               "frac": ftle_gbs / hbm_peak, "traffic": ftle_traffic, "kernel": "ftle_kernel",
                               "kernel_ms": ft_ms, "peak_source": hbm_src, "bytes_per_point": 24},
+            "parity": parity,
             "ridge_tail": ridge,
             "cpu_baseline": cpu,
             "clocks": clocks,
             "halo_exchange_ms": halo_ms if world > 1 else 0.0,
+            "gather_ms": gather_ms,
+            "planning_ms": plan_ms if world > 1 else 0.0,
             "wall_ms_per_step": t_wall / K * 1e3,
             "ftle_checksum": checksum,
             "fp64_peak_tflops_measured": fp64_peak,
+            "library": _lib.library_info(),
         }
+        if world > 1:
+            line["gather"] = {"ms": gather_ms, "bytes_into_rank0": int(8 * (n - (blocks[0][1] - blocks[0][0])) * n),
+                              "GBps": 8.0 * (n - (blocks[0][1] - blocks[0][0])) * n / (gather_ms * 1e-3) / 1e9,
+                              "checksum": gathered_checksum,
+                              "how": "sharded.gather_rows: one NCCL irecv per peer straight into the rows of the "
+                                     "assembled [n, n] FTLE field on rank 0, best of 3, max over ranks"}
         sys.stdout.flush()
         if saved_stdout is not None:
             os.dup2(saved_stdout, 1)
@@ -422,6 +620,87 @@ def run_b200(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def parity_block(args, n, world, rank, blocks, slab, own, ftle, HW, has_lo, f, params, x_dev, y_dev, dx, dy):
+    """Oracle rows against the GPU's rows of the same grid (rank 0 reports).  The sample is a
+    contiguous row range: at N = 1 the cpu_baseline sample; at N > 1 a shorter one that straddles
+    the cut between rank 0 and rank 1, whose upper half rank 1 sends over."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from parity_common import compare_flowmaps, ftle_rel_l2
+    from numbacs_b200.integration import flowmap_grid_2D
+    from numbacs_b200.diagnostics import ftle_grid_2D
+    if world == 1:
+        rows_s = args.cpu_rows or pick_rows(n, CPU_TARGET_S)
+        a = n // 4
+    else:
+        rows_s = min(args.cpu_rows or 256, 2 * min(blocks[0][1] - blocks[0][0], blocks[1][1] - blocks[1][0]))
+        rows_s = max(8, rows_s // 2 * 2)
+        a = blocks[0][1] - rows_s // 2
+    b = a + rows_s
+    # the GPU's rows [a, b) of the step's flow map and FTLE field, assembled on rank 0
+    gpu_fm = gpu_ft = None
+    if world == 1:
+        gpu_fm, gpu_ft = own[a:b], ftle[a:b]
+    else:
+        cut = blocks[0][1]
+        if rank == 0:
+            hi_fm = torch.empty((b - cut, n, 2), dtype=torch.float64, device="cuda")
+            hi_ft = torch.empty((b - cut, n), dtype=torch.float64, device="cuda")
+            dist.recv(hi_fm, src=1)
+            dist.recv(hi_ft, src=1)
+            gpu_fm = torch.cat([own[a:cut], hi_fm])
+            gpu_ft = torch.cat([ftle[a:cut], hi_ft])
+        elif rank == 1:
+            dist.send(own[:b - cut].contiguous(), dst=0)
+            dist.send(ftle[:b - cut].contiguous(), dst=0)
+    parity = cpu = None
+    if rank == 0:
+        reps = 3 if world == 1 else 1
+        r = cpu_sample(n, rows_s, reps=reps, i0=a, keep=True)
+        # per-particle step counts of the GPU for the sample rows: one extra (untimed) launch on
+        # those rows; its positions must be bit-identical to the rows of the timed full-grid launch
+        info = {}
+        fm_s = flowmap_grid_2D(f, T0, TINT, x_dev[a:b].contiguous(), y_dev, params, rtol=RTOL, atol=ATOL,
+                               info=info, device_out=True)
+        identical = bool(torch.equal(fm_s, gpu_fm))
+        st = info["steps"].cpu().numpy()
+        res, same = compare_flowmaps(gpu_fm.cpu().numpy(), st, r["fm"], r["steps"], (2.0, 1.0))
+        # FTLE rows a+1 .. b-2 have their full stencil inside the sample
+        ft_gpu = gpu_ft[1:-1].cpu().numpy()
+        keep_rows = slice(1, rows_s - 1)
+        # the oracle's FTLE of the block treats its first / last row as borders; compare interior rows
+        bad = ~same
+        touch = bad.copy()
+        touch[1:] |= bad[:-1]
+        touch[:-1] |= bad[1:]
+        touch[:, 1:] |= bad[:, :-1]
+        touch[:, :-1] |= bad[:, 1:]
+        keep = ~touch[keep_rows]
+        fto = r["ftle"][keep_rows]
+        den = np.linalg.norm(fto[keep])
+        res.update({
+            "rows": [int(a), int(b)], "straddles_rank_cut": world > 1,
+            "sample_rows_bit_identical_to_full_grid_launch": identical,
+            "ftle_rel_l2": float(np.linalg.norm((ft_gpu - fto)[keep]) / den) if den > 0 else 0.0,
+            "ftle_pixels_compared": int(keep.sum()), "ftle_pixels_excluded": int((~keep).sum()),
+            "ftle_max_abs_diff": float(np.abs(ft_gpu - fto)[keep].max()),
+            "gates": {"max_rel_dx_matching": 1e-8, "ftle_rel_l2": 1e-6, "mismatch_fraction": 1e-5},
+            "oracle": "oracle/ C restatement, glibc libm, unfused arithmetic, same rtol/atol",
+        })
+        res["pass"] = bool(identical and res["max_rel_dx_matching"] <= 1e-8 and res["ftle_rel_l2"] <= 1e-6
+                           and res["mismatch_fraction"] <= 1e-5)
+        parity = res
+        if world == 1:
+            cpu = {"value": r["pps"], "unit": "grid points/s", "cores": r["threads"], "kind": "port",
+                   "sample": f"{rows_s} contiguous rows x {n} columns of the same grid "
+                             f"({rows_s * n} particles, best of 3: {r['seconds']:.1f} s), oracle/ C port with OpenMP",
+                   "host_cpus": os.cpu_count()}
+    if world > 1:
+        dist.barrier()
+    return parity, cpu
 
 
 def main():

@@ -72,5 +72,18 @@ def build(force=False, verbose=False, extra_flags=(), lib=LIB, objdir=OBJ):
     return lib
 
 
+STRICT_LIB = os.path.join(HERE, "libb200cs_strict.so")
+STRICT_FLAGS = ["-DB200CS_STRICT=1", "-fmad=false"]
+
+
+def build_strict(force=False, verbose=False):
+    """The parity-calibration build (csrc/dop853.cuh, B200CS_STRICT): reference evaluation order,
+    separately rounded operations, CUDA libm.  Test infrastructure: the product never loads it."""
+    return build(force=force, verbose=verbose, extra_flags=STRICT_FLAGS, lib=STRICT_LIB,
+                 objdir=os.path.join(CSRC, "build_strict"))
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    if "--strict" in sys.argv:
+        print(build_strict(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

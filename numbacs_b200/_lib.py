@@ -69,26 +69,61 @@ PROTOTYPES = {
 }
 
 _lib = None
+_lib_path = None
+# the parity-calibration build of the same sources (B200CS_STRICT, csrc/dop853.cuh): test infrastructure
+STRICT_LIB_PATH = os.path.join(_HERE, "libb200cs_strict.so")
+
+
+def _open(path):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} is missing: build the CUDA library first "
+            "(python -m numbacs_b200._build, or __graft_entry__.build()). "
+            "numbacs_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    L.b200cs_last_error.restype = C.c_char_p
+    L.b200cs_last_error.argtypes = []
+    for name, argtypes in PROTOTYPES.items():
+        fn = getattr(L, name)
+        fn.restype = C.c_int
+        fn.argtypes = argtypes
+    return L
 
 
 def load():
     """Load libb200cs.so; raises if it has not been built (python -m numbacs_b200._build)."""
-    global _lib
+    global _lib, _lib_path
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise RuntimeError(
-                f"{LIB_PATH} is missing: build the CUDA library first "
-                "(python -m numbacs_b200._build, or __graft_entry__.build()). "
-                "numbacs_b200 has no CPU fallback.")
-        L = C.CDLL(LIB_PATH)
-        L.b200cs_last_error.restype = C.c_char_p
-        L.b200cs_last_error.argtypes = []
-        for name, argtypes in PROTOTYPES.items():
-            fn = getattr(L, name)
-            fn.restype = C.c_int
-            fn.argtypes = argtypes
-        _lib = L
+        _lib = _open(LIB_PATH)
+        _lib_path = LIB_PATH
     return _lib
+
+
+def library_info():
+    """Which shared library the API is bound to, and whether B200CS_LIB replaced the product one."""
+    load()
+    return {"path": _lib_path, "overridden_by_B200CS_LIB": bool(os.environ.get("B200CS_LIB")),
+            "version": int(_lib.b200cs_version())}
+
+
+class use_library:
+    """Context manager for tests / A-B tools: bind the whole Python API to another build of the
+    library (e.g. STRICT_LIB_PATH).  Flow handles belong to the library that created them, so
+    create the flows inside the block."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        global _lib, _lib_path
+        self.saved = (_lib, _lib_path)
+        _lib, _lib_path = _open(self.path), self.path
+        return _lib
+
+    def __exit__(self, *exc):
+        global _lib, _lib_path
+        _lib, _lib_path = self.saved
+        return False
 
 
 def check(rc):

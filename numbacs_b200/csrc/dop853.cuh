@@ -37,6 +37,23 @@
 
 #include "dop853_tableau.cuh"
 
+// B200CS_STRICT: the parity-calibration build (tools/build_variant.py strict -DB200CS_STRICT=1
+// -fmad=false, tests/test_gpu_parity_atsize.py).  Every expression of the integrator and of the
+// right-hand sides is evaluated in the reference's (= the oracle's) order with separately rounded
+// IEEE multiplications and additions, IEEE division / sqrt and CUDA libm sin / cos / cosh / tanh /
+// pow.  What is left between this build and the CPU oracle is the difference between two libms
+// (each <= 1-2 ulp): the distance no GPU implementation can go below, and the yardstick the
+// product build's distance to the oracle is compared with.
+#ifndef B200CS_STRICT
+#define B200CS_STRICT 0
+#endif
+#ifndef B200CS_STRICT_INT   // the integrator half of the strict build on its own (A/B decomposition)
+#define B200CS_STRICT_INT B200CS_STRICT
+#endif
+#if B200CS_STRICT_INT
+#define B200CS_LEAN 0
+#define B200CS_LEAN2 0
+#endif
 #ifndef B200CS_LEAN
 #define B200CS_LEAN 1
 #endif
@@ -68,6 +85,15 @@ struct rhs_affine<T, std::void_t<decltype(T::kAuxAffine)>> : std::bool_constant<
 
 namespace detail {
 
+// a*b + c: one FMA in the product build, two roundings (the reference's arithmetic) in the strict one
+__device__ __forceinline__ double mad(double a, double b, double c) {
+#if B200CS_STRICT_INT
+    return __dadd_rn(__dmul_rn(a, b), c);
+#else
+    return fma(a, b, c);
+#endif
+}
+
 // err^(1/8) with three correctly rounded square roots (libm pow in the reference; the difference
 // is <= 1 ulp and only scales the next step size)
 #if B200CS_LEAN2
@@ -77,6 +103,8 @@ namespace detail {
 // few dozen attempts, exactly as with sqrt); +inf gives NaN, which the same fmin treats like +inf.
 __device__ __forceinline__ double sqrt_fast(double x) { return x == 0.0 ? 0.0 : x * rsqrt(x); }
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt_fast(sqrt_fast(sqrt_fast(x))); }
+#elif B200CS_STRICT_INT
+__device__ __forceinline__ double pow_eighth(double x) { return pow(x, 0.125); }  // libm pow, as the reference
 #else
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
 #endif
@@ -94,8 +122,8 @@ __device__ __forceinline__ void stage_arg(double (&yy)[N], const double (&y)[N],
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double acc = 0.0;
-        ((dop::a(S, J + 1) != 0.0 ? (void)(acc = fma(dop::kTab.a[S][J + 1], K[J + 1][i], acc)) : (void)0), ...);
-        yy[i] = fma(h, acc, y[i]);
+        ((dop::a(S, J + 1) != 0.0 ? (void)(acc = mad(dop::kTab.a[S][J + 1], K[J + 1][i], acc)) : (void)0), ...);
+        yy[i] = mad(h, acc, y[i]);
     }
 }
 
@@ -105,7 +133,7 @@ __device__ __forceinline__ void do_stage(const Rhs &rhs, double aux, double x, d
                                          double (&K)[17][N]) {
     double yy[N];
     stage_arg<S, N>(yy, y, h, K, std::make_integer_sequence<int, S - 1>{});
-    rhs.eval(aux, fma(dop::kTab.c[S], h, x), yy, K[S]);
+    rhs.eval(aux, mad(dop::kTab.c[S], h, x), yy, K[S]);
 }
 
 // time-only part of the RHS at the stage times S0 .. S0+M-1 of the step (x, h), M chains at once
@@ -119,7 +147,7 @@ __device__ __forceinline__ void stage_aux(const Rhs &rhs, double x, double h, do
             rhs.template time_part_affine<M>(x, h, t, a);
         } else {
 #pragma unroll
-            for (int m = 0; m < M; ++m) t[m] = fma(dop::kTab.c[S0 + m], h, x);
+            for (int m = 0; m < M; ++m) t[m] = mad(dop::kTab.c[S0 + m], h, x);
             rhs.template time_part<M>(t, a);
         }
 #pragma unroll
@@ -130,7 +158,7 @@ __device__ __forceinline__ void stage_aux(const Rhs &rhs, double x, double h, do
 template <int R, int N, int... J>
 __device__ __forceinline__ double dense_row(const double (&K)[17][N], int i, std::integer_sequence<int, J...>) {
     double acc = 0.0;
-    ((dop::d(R, J + 1) != 0.0 ? (void)(acc = fma(dop::kTab.d[R][J + 1], K[J + 1][i], acc)) : (void)0), ...);
+    ((dop::d(R, J + 1) != 0.0 ? (void)(acc = mad(dop::kTab.d[R][J + 1], K[J + 1][i], acc)) : (void)0), ...);
     return acc;
 }
 
@@ -186,25 +214,25 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         double dnf = 0.0, dny = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double sk = fma(rtol, fabs(y[i]), atol);
+            const double sk = detail::mad(rtol, fabs(y[i]), atol);
             const double a = K[1][i] / sk, b = y[i] / sk;
-            dnf = fma(a, a, dnf);
-            dny = fma(b, b, dny);
+            dnf = detail::mad(a, a, dnf);
+            dny = detail::mad(b, b, dny);
         }
         h = (dnf <= 1.0e-10 || dny <= 1.0e-10) ? 1.0e-6 : sqrt(dny / dnf) * 0.01;
         h = fmin(h, hmax) * posneg;
         double y1[N], f1[N];
 #pragma unroll
-        for (int i = 0; i < N; ++i) y1[i] = fma(h, K[1][i], y[i]);
+        for (int i = 0; i < N; ++i) y1[i] = detail::mad(h, K[1][i], y[i]);
         double t1[1] = {x + h}, a1[1] = {0.0};
         if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
         rhs.eval(a1[0], x + h, y1, f1);
         double der2 = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double sk = fma(rtol, fabs(y[i]), atol);
+            const double sk = detail::mad(rtol, fabs(y[i]), atol);
             const double a = (f1[i] - K[1][i]) / sk;
-            der2 = fma(a, a, der2);
+            der2 = detail::mad(a, a, der2);
         }
         der2 = sqrt(der2) / h;
         const double der12 = fmax(fabs(der2), sqrt(dnf));
@@ -257,41 +285,41 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             double s = dop::kTab.b[1] * K[1][i];
-            s = fma(dop::kTab.b[6], K[6][i], s);
-            s = fma(dop::kTab.b[7], K[7][i], s);
-            s = fma(dop::kTab.b[8], K[8][i], s);
-            s = fma(dop::kTab.b[9], K[9][i], s);
-            s = fma(dop::kTab.b[10], K[10][i], s);
-            s = fma(dop::kTab.b[11], K[11][i], s);
-            s = fma(dop::kTab.b[12], K[12][i], s);
-            y5[i] = fma(h, s, y[i]);
-            const double sk = fma(rtol, fmax(fabs(y[i]), fabs(y5[i])), atol);
-            double e3 = fma(-dop::kTab.bhh[0], K[1][i], s);
-            e3 = fma(-dop::kTab.bhh[1], K[9][i], e3);
-            e3 = fma(-dop::kTab.bhh[2], K[12][i], e3);
+            s = detail::mad(dop::kTab.b[6], K[6][i], s);
+            s = detail::mad(dop::kTab.b[7], K[7][i], s);
+            s = detail::mad(dop::kTab.b[8], K[8][i], s);
+            s = detail::mad(dop::kTab.b[9], K[9][i], s);
+            s = detail::mad(dop::kTab.b[10], K[10][i], s);
+            s = detail::mad(dop::kTab.b[11], K[11][i], s);
+            s = detail::mad(dop::kTab.b[12], K[12][i], s);
+            y5[i] = detail::mad(h, s, y[i]);
+            const double sk = detail::mad(rtol, fmax(fabs(y[i]), fabs(y5[i])), atol);
+            double e3 = detail::mad(-dop::kTab.bhh[0], K[1][i], s);
+            e3 = detail::mad(-dop::kTab.bhh[1], K[9][i], e3);
+            e3 = detail::mad(-dop::kTab.bhh[2], K[12][i], e3);
 #if B200CS_LEAN
             const double rsk = 1.0 / sk;  // one reciprocal serves both estimates (<= 1 ulp from e/sk)
             e3 *= rsk;
 #else
             e3 /= sk;
 #endif
-            err2 = fma(e3, e3, err2);
+            err2 = detail::mad(e3, e3, err2);
             double e5 = dop::kTab.er[1] * K[1][i];
-            e5 = fma(dop::kTab.er[6], K[6][i], e5);
-            e5 = fma(dop::kTab.er[7], K[7][i], e5);
-            e5 = fma(dop::kTab.er[8], K[8][i], e5);
-            e5 = fma(dop::kTab.er[9], K[9][i], e5);
-            e5 = fma(dop::kTab.er[10], K[10][i], e5);
-            e5 = fma(dop::kTab.er[11], K[11][i], e5);
-            e5 = fma(dop::kTab.er[12], K[12][i], e5);
+            e5 = detail::mad(dop::kTab.er[6], K[6][i], e5);
+            e5 = detail::mad(dop::kTab.er[7], K[7][i], e5);
+            e5 = detail::mad(dop::kTab.er[8], K[8][i], e5);
+            e5 = detail::mad(dop::kTab.er[9], K[9][i], e5);
+            e5 = detail::mad(dop::kTab.er[10], K[10][i], e5);
+            e5 = detail::mad(dop::kTab.er[11], K[11][i], e5);
+            e5 = detail::mad(dop::kTab.er[12], K[12][i], e5);
 #if B200CS_LEAN
             e5 *= rsk;
 #else
             e5 /= sk;
 #endif
-            err = fma(e5, e5, err);
+            err = detail::mad(e5, e5, err);
         }
-        double deno = fma(0.01, err2, err);
+        double deno = detail::mad(0.01, err2, err);
         if (deno <= 0.0) deno = 1.0;
 #if B200CS_LEAN
         err = fabs(h) * err * rsqrt(deno * (double)N);
@@ -319,7 +347,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                         rc[0][i] = y[i];
                         const double ydiff = y5[i] - y[i];
                         rc[1][i] = ydiff;
-                        const double bspl = fma(h, K[1][i], -ydiff);
+                        const double bspl = detail::mad(h, K[1][i], -ydiff);
                         rc[2][i] = bspl;
                         rc[3][i] = ydiff - h * K[13][i] - bspl;
                     }

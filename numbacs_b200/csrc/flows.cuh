@@ -56,6 +56,30 @@ struct RhsParams {
 // DAMPED = false is the flow with alpha == 0 (the default parameters, and every example of the
 // reference): the launcher picks the instantiation, so the hot loop carries neither the damping
 // terms nor a test for them.
+#if B200CS_STRICT_RHS
+// Parity-calibration build: the reference's expressions (flows.py:1152-1158) token for token, every
+// operation rounded separately (-fmad=false), CUDA libm sin / cos.
+template <bool DAMPED>
+struct DoubleGyreT {
+    static constexpr int N = 2;
+    static constexpr int kAux = 0;
+    const RhsParams &P;
+    __device__ __forceinline__ explicit DoubleGyreT(const RhsParams &P_) : P(P_) {}
+    template <int M>
+    __device__ __forceinline__ void time_part(const double (&)[M], double (&)[M]) const {}
+    __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
+        const double *p = P.p;
+        const double pi = kPi;
+        const double tt = p[0] * t;
+        const double a = p[2] * sin(p[4] * tt + p[5]);
+        const double b = 1 - 2 * a;
+        const double f = a * (y[0] * y[0]) + b * y[0];
+        const double df = 2 * a * y[0] + b;
+        dy[0] = p[0] * (-pi * p[1] * sin(pi * f) * cos(pi * y[1]) - p[3] * y[0]);
+        dy[1] = p[0] * (pi * p[1] * cos(pi * f) * sin(pi * y[1]) * df - p[3] * y[1]);
+    }
+};
+#else
 template <bool DAMPED>
 struct DoubleGyreT {
     static constexpr int N = 2;
@@ -151,6 +175,7 @@ struct DoubleGyreT {
         }
     }
 };
+#endif  // B200CS_STRICT_RHS
 using DoubleGyre = DoubleGyreT<false>;
 using DoubleGyreDamped = DoubleGyreT<true>;
 
@@ -164,6 +189,22 @@ struct BickleyJet {
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
         const double *p = P.p;
         const double tt = p[0] * t;
+#if B200CS_STRICT_RHS
+        {   // flows.py:1189-1213 token for token (cosh(Y) ** 2 is cosh(Y) * cosh(Y) in numba)
+            const double Y = y[1] / p[2];
+            const double ch = cosh(Y);
+            const double sech2 = 1 / (ch * ch);
+            dy[0] = p[0] * (p[1] * sech2 +
+                            2 * p[1] * tanh(Y) * sech2 *
+                                (p[3] * cos(p[6] * (y[0] - p[9] * tt)) + p[4] * cos(p[7] * (y[0] - p[10] * tt)) +
+                                 p[5] * cos(p[8] * (y[0] - p[11] * tt))));
+            dy[1] = -p[0] * (p[1] * p[2] * sech2 *
+                             (p[3] * p[6] * sin(p[6] * (y[0] - p[9] * tt)) +
+                              p[4] * p[7] * sin(p[7] * (y[0] - p[10] * tt)) +
+                              p[5] * p[8] * sin(p[8] * (y[0] - p[11] * tt))));
+            return;
+        }
+#endif
 #if B200CS_BICKLEY_WIDE
         // y1 / L_y with the reciprocal from the host and one FMA residual correction: the correctly
         // rounded quotient in three instructions (the divisor is a launch constant)
@@ -203,7 +244,7 @@ struct BickleyJet {
 
 struct Abc {
     static constexpr int N = 3;
-    static constexpr int kAux = 1;
+    static constexpr int kAux = B200CS_STRICT_RHS ? 0 : 1;
     const RhsParams &P;
     __device__ __forceinline__ explicit Abc(const RhsParams &P_) : P(P_) {}
     // A(t) = p1 + p4 * tt * sin(pi*tt)   (flows.py:1256-1257)
@@ -223,8 +264,18 @@ struct Abc {
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = fma(p[4] * (p[0] * t[m]), st[m], p[1]);
     }
-    __device__ __forceinline__ void eval(double At, double, const double (&y)[3], double (&dy)[3]) const {
+    __device__ __forceinline__ void eval(double At, double t, const double (&y)[3], double (&dy)[3]) const {
         const double *p = P.p;
+#if B200CS_STRICT_RHS
+        {   // flows.py:1255-1258 token for token
+            const double pi = kPi;
+            const double tt = p[0] * t;
+            dy[0] = p[0] * ((p[1] + p[4] * tt * sin(pi * tt)) * sin(y[2]) + p[3] * cos(y[1]));
+            dy[1] = p[0] * (p[2] * sin(y[0]) + (p[1] + p[4] * tt * sin(pi * tt)) * cos(y[1]));
+            dy[2] = p[0] * (p[3] * sin(y[1]) + p[2] * cos(y[1]));
+            return;
+        }
+#endif
         const double arg[2] = {y[0], y[2]};
         double s02[2], s1, c1;
 #if B200CS_ABC_WIDE
@@ -270,7 +321,11 @@ struct Spline2D {
         else eval_spline_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
         if (SPHERICAL) {
             // ((p0*u)*180) / (pi*r*cos(yy*pi/180))   (flows.py:165-196)
+#if B200CS_STRICT_RHS
+            dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos(yy * kPi / 180.0));
+#else
             dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos_fast(yy * kPi / 180.0));
+#endif
             dy[1] = ((p0 * v) * 180.0) / (kPi * P.r);
         } else {
             dy[0] = p0 * u;

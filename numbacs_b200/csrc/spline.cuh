@@ -11,6 +11,13 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef B200CS_STRICT
+#define B200CS_STRICT 0
+#endif
+#ifndef B200CS_STRICT_RHS   // the right-hand-side half of the strict build on its own (A/B decomposition)
+#define B200CS_STRICT_RHS B200CS_STRICT
+#endif
+
 namespace b200cs {
 
 struct SplineGridDev {
@@ -27,17 +34,46 @@ struct SplineGridDev {
 // (the product i*delta is rounded before the subtraction, as in unfused CPU arithmetic)
 __device__ __forceinline__ void axis_locate(const SplineGridDev &g, int d, double x, int &i, double &lam) {
     const double dd = x - g.a[d];
+#if B200CS_STRICT_RHS
+    // the oracle's arithmetic: true divisions by delta = (b - a)/(n - 1)
+    const double delta = g.delta[d];
+    double fi = floor(dd / delta);
+    fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
+    i = (int)fi;
+    lam = __dsub_rn(dd, __dmul_rn(fi, delta)) / delta;
+#else
     double fi = floor(dd * g.inv_delta[d]);
     fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
     i = (int)fi;
     const double r = __dsub_rn(dd, __dmul_rn(fi, g.delta[d]));
     lam = r * g.inv_delta[d];
+#endif
+}
+
+// a*b + c: one FMA, or two roundings in the parity-calibration build (dop853.cuh, B200CS_STRICT)
+__device__ __forceinline__ double sp_mad(double a, double b, double c) {
+#if B200CS_STRICT_RHS
+    return __dadd_rn(__dmul_rn(a, b), c);
+#else
+    return fma(a, b, c);
+#endif
 }
 
 // uniform cubic B-spline blending weights; outside [0,1] they continue linearly when the
 // extrapolation mode is 'linear'.
 __device__ __forceinline__ void bspline_weights(double l, bool linear_ext, double (&P)[4]) {
     const double s = 1.0 / 6.0;
+#if B200CS_STRICT_RHS
+    if (!(linear_ext && (l < 0.0 || l > 1.0))) {
+        // the CPU restatement's evaluation order (Horner-free, left to right)
+        const double l2 = l * l, l3 = l2 * l;
+        P[0] = (-1.0 / 6.0) * l3 + (3.0 / 6.0) * l2 + (-3.0 / 6.0) * l + 1.0 / 6.0;
+        P[1] = (3.0 / 6.0) * l3 + (-6.0 / 6.0) * l2 + 4.0 / 6.0;
+        P[2] = (-3.0 / 6.0) * l3 + (3.0 / 6.0) * l2 + (3.0 / 6.0) * l + 1.0 / 6.0;
+        P[3] = (1.0 / 6.0) * l3;
+        return;
+    }
+#endif
     if (linear_ext && l < 0.0) {
         P[0] = fma(-0.5, l, s);
         P[1] = 4.0 * s;
@@ -94,13 +130,13 @@ __device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const dou
         for (int b = 0; b < 4; ++b) {
             const double2 *c = base + a * g.s0 + b * g.s1;
             const double2 c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2), c3 = __ldg(c + 3);
-            const double cu = fma(P2[3], c3.x, fma(P2[2], c2.x, fma(P2[1], c1.x, P2[0] * c0.x)));
-            const double cv = fma(P2[3], c3.y, fma(P2[2], c2.y, fma(P2[1], c1.y, P2[0] * c0.y)));
-            bu = fma(P1[b], cu, bu);
-            bv = fma(P1[b], cv, bv);
+            const double cu = sp_mad(P2[3], c3.x, sp_mad(P2[2], c2.x, sp_mad(P2[1], c1.x, P2[0] * c0.x)));
+            const double cv = sp_mad(P2[3], c3.y, sp_mad(P2[2], c2.y, sp_mad(P2[1], c1.y, P2[0] * c0.y)));
+            bu = sp_mad(P1[b], cu, bu);
+            bv = sp_mad(P1[b], cv, bv);
         }
-        au = fma(P0[a], bu, au);
-        av = fma(P0[a], bv, av);
+        au = sp_mad(P0[a], bu, au);
+        av = sp_mad(P0[a], bv, av);
     }
     u = au;
     v = av;
@@ -129,10 +165,10 @@ __device__ __forceinline__ double eval_spline_s(const SplineGridDev &g, const do
         for (int b = 0; b < 4; ++b) {
             const double *c = base + a * g.s0 + b * g.s1;
             const double acc2 =
-                fma(P2[3], __ldg(c + 3), fma(P2[2], __ldg(c + 2), fma(P2[1], __ldg(c + 1), P2[0] * __ldg(c))));
-            acc1 = fma(P1[b], acc2, acc1);
+                sp_mad(P2[3], __ldg(c + 3), sp_mad(P2[2], __ldg(c + 2), sp_mad(P2[1], __ldg(c + 1), P2[0] * __ldg(c))));
+            acc1 = sp_mad(P1[b], acc2, acc1);
         }
-        acc0 = fma(P0[a], acc1, acc0);
+        acc0 = sp_mad(P0[a], acc1, acc0);
     }
     return acc0;
 }
@@ -160,11 +196,11 @@ __device__ __forceinline__ void eval_linear_uv(const SplineGridDev &g, const dou
             const double wb = b ? l1 : 1.0 - l1;
             const double2 *cc = c + a * g.s0 + b * g.s1;
             const double2 c0 = __ldg(cc), c1 = __ldg(cc + 1);
-            vu = fma(wb, fma(l2, c1.x, m2 * c0.x), vu);
-            vv = fma(wb, fma(l2, c1.y, m2 * c0.y), vv);
+            vu = sp_mad(wb, sp_mad(l2, c1.x, m2 * c0.x), vu);
+            vv = sp_mad(wb, sp_mad(l2, c1.y, m2 * c0.y), vv);
         }
-        u = fma(wa, vu, u);
-        v = fma(wa, vv, v);
+        u = sp_mad(wa, vu, u);
+        v = sp_mad(wa, vv, v);
     }
 }
 
@@ -187,9 +223,9 @@ __device__ __forceinline__ double eval_linear_s(const SplineGridDev &g, const do
         for (int b = 0; b < 2; ++b) {
             const double wb = b ? l1 : 1.0 - l1;
             const double *cc = c + a * g.s0 + b * g.s1;
-            va = fma(wb, fma(l2, __ldg(cc + 1), (1.0 - l2) * __ldg(cc)), va);
+            va = sp_mad(wb, sp_mad(l2, __ldg(cc + 1), (1.0 - l2) * __ldg(cc)), va);
         }
-        v = fma(wa, va, v);
+        v = sp_mad(wa, va, v);
     }
     return v;
 }

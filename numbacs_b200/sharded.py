@@ -27,8 +27,13 @@ def row_block(nx, world_size, rank):
     return i0, i0 + base + (1 if rank < rem else 0)
 
 
-def balanced_row_blocks(cost_per_row, world_size):
+def balanced_row_blocks(cost_per_row, world_size, min_rows=1):
     """Contiguous row blocks [(i0, i1)] * world_size with (nearly) equal summed cost.
+
+    Every rank gets at least `min_rows` rows (1 for the FTLE halo exchange, which talks to the
+    immediate neighbour only; 2 for the ridge tail's two-row halo), so no empty block can sit
+    between two non-empty ones; with fewer than world_size * min_rows rows the equal-size
+    partition of row_block() is returned (empty blocks only at the end).
 
     The adaptive integrator does not spend the same time on every particle (7-23 step attempts on
     the double gyre), and the cost varies smoothly with x, so equal-sized row blocks leave the GPUs
@@ -45,22 +50,39 @@ def balanced_row_blocks(cost_per_row, world_size):
     cuts = np.where((cuts > 0) & (np.abs(cum[np.maximum(cuts - 1, 0)] - targets) < np.abs(cum[np.minimum(cuts, nx)] - targets)),
                     cuts - 1, cuts)
     cuts = np.clip(np.maximum.accumulate(cuts), 0, nx)
+    if nx < world_size * min_rows:
+        return [row_block(nx, world_size, r) for r in range(world_size)]
     edges = [0] + [int(v) for v in cuts] + [nx]
+    for r in range(1, world_size):          # forward pass: every block at least min_rows
+        edges[r] = max(edges[r], edges[r - 1] + min_rows)
+    for r in range(world_size - 1, 0, -1):  # backward pass: leave room for the blocks above
+        edges[r] = min(edges[r], edges[r + 1] - min_rows)
     return [(edges[r], edges[r + 1]) for r in range(world_size)]
 
 
 def estimate_row_cost(funcptr, t0, T, x, y, params, rtol=1e-6, atol=1e-8, rows=256, cols=256):
     """Step attempts per row of the (x, y) grid, estimated by integrating a rows x cols subsample
-    (a fraction of a millisecond on the GPU) and interpolating along x."""
+    (a fraction of a millisecond on the GPU) and interpolating along x.
+
+    With CUDA tensors for x and y everything stays on the device -- the subsample is gathered, the
+    per-particle step counts are reduced per row there, and only `rows` doubles come back -- so
+    the whole planning pass costs about a millisecond and can sit inside an end-to-end step."""
     from .integration import flowmap_grid_2D
-    x = np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)
-    y = np.asarray(y.cpu() if hasattr(y, "cpu") else y, dtype=np.float64)
     nx, ny = len(x), len(y)
     ix = np.unique(np.linspace(0, nx - 1, min(rows, nx)).round().astype(np.int64))
     iy = np.unique(np.linspace(0, ny - 1, min(cols, ny)).round().astype(np.int64))
     info = {}
-    flowmap_grid_2D(funcptr, t0, T, x[ix], y[iy], params, rtol=rtol, atol=atol, info=info)
-    per_row = np.asarray(info["steps"]).sum(axis=(1, 2)).astype(np.float64) / len(iy)
+    if hasattr(x, "is_cuda") and x.is_cuda and hasattr(y, "is_cuda") and y.is_cuda:
+        import torch
+        xs = x[torch.as_tensor(ix, device=x.device)]
+        ys = y[torch.as_tensor(iy, device=y.device)]
+        flowmap_grid_2D(funcptr, t0, T, xs, ys, params, rtol=rtol, atol=atol, info=info, device_out=True)
+        per_row = (info["steps"].sum(dim=(1, 2), dtype=torch.float64) / len(iy)).cpu().numpy()
+    else:
+        x = np.asarray(x.cpu() if hasattr(x, "cpu") else x, dtype=np.float64)
+        y = np.asarray(y.cpu() if hasattr(y, "cpu") else y, dtype=np.float64)
+        flowmap_grid_2D(funcptr, t0, T, x[ix], y[iy], params, rtol=rtol, atol=atol, info=info)
+        per_row = np.asarray(info["steps"]).sum(axis=(1, 2)).astype(np.float64) / len(iy)
     return np.interp(np.arange(nx), ix, per_row)
 
 
@@ -283,24 +305,47 @@ def gather_points(pts, group=None, dst=0):
     return torch.cat([bufs[r][:int(counts[r])] for r in range(world)], dim=0)
 
 
-def gather_rows(block, nx, group=None, dst=0):
-    """Gather row blocks [rows_r, ...] of every rank into the full [nx, ...] array on `dst`
-    (None elsewhere).  Blocks may differ in size by one row, so they are padded to a common size."""
+def gather_rows(block, nx, group=None, dst=0, blocks=None, out=None):
+    """Assemble the row blocks [rows_r, ...] of every rank into the full [nx, ...] array on `dst`
+    (None elsewhere): the final gather of the sharded path.
+
+    `blocks` is the list of (i0, i1) per rank the blocks were computed with (balanced_row_blocks
+    or the default row_block partition); sizes may differ arbitrarily.  The receiving rank posts
+    one irecv per peer STRAIGHT INTO the rows of the assembled array (no padding, no staging copy,
+    every peer's block arrives over its own NVLink path at the same time) and copies its own
+    block; the other ranks post one isend.  `out` optionally supplies the [nx, ...] destination on
+    `dst` (e.g. a buffer reused across frames)."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if blocks is None:
+        blocks = [row_block(nx, world, r) for r in range(world)]
+    if len(blocks) != world or blocks[0][0] != 0 or blocks[-1][1] != nx or \
+            any(blocks[r][1] != blocks[r + 1][0] for r in range(world - 1)):
+        raise ValueError(f"blocks {blocks} do not tile [0, {nx}) over {world} ranks")
+    i0, i1 = blocks[rank]
+    if block.shape[0] != i1 - i0:
+        raise ValueError(f"rank {rank} holds {block.shape[0]} rows, its block {blocks[rank]} has {i1 - i0}")
     if world == 1:
-        return block
-    max_rows = -(-nx // world)
-    pad = torch.zeros((max_rows,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
-    pad[:block.shape[0]] = block
-    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
-    dist.gather(pad, bufs, dst=dst, group=group)
-    if rank != dst:
-        return None
-    parts = []
-    for r in range(world):
-        a, b = row_block(nx, world, r)
-        parts.append(bufs[r][:b - a])
-    return torch.cat(parts, dim=0)
+        if out is None:
+            return block
+        out.copy_(block)
+        return out
+    block = block.contiguous()
+    ops = []
+    if rank == dst:
+        if out is None:
+            out = torch.empty((nx,) + tuple(block.shape[1:]), dtype=block.dtype, device=block.device)
+        for r in range(world):
+            a, b = blocks[r]
+            if r != dst and b > a:
+                ops.append(dist.P2POp(dist.irecv, out[a:b], r, group))
+    elif i1 > i0:
+        ops.append(dist.P2POp(dist.isend, block, dst, group))
+    reqs = dist.batch_isend_irecv(ops) if ops else []
+    if rank == dst and i1 > i0:
+        out[i0:i1].copy_(block)
+    for req in reqs:
+        req.wait()
+    return out if rank == dst else None

@@ -100,6 +100,7 @@ def lib():
                                             C.c_void_p, C.c_double, C.c_double, C.c_double,
                                             C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_flowmap_composition.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.oracle_scalar_eval_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
         _lib = L
@@ -157,9 +158,10 @@ class Scalar:
             pass
 
     def __call__(self, pts):
-        pts = np.atleast_2d(_f64(pts))
-        fn = lib().oracle_eval_linear3 if self.linear else lib().oracle_eval_spline3
-        return np.array([fn(self.handle, *map(float, q)) for q in pts])
+        pts = np.ascontiguousarray(np.atleast_2d(_f64(pts)))
+        out = np.empty(len(pts))
+        lib().oracle_scalar_eval_many(self.handle, int(self.linear), _ptr(pts), len(pts), _ptr(out))
+        return out
 
 
 def default_params(flow_str, int_direction=1.0):

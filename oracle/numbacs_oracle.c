@@ -639,6 +639,15 @@ double oracle_composite_simpsons(const double *f, int64_t len, double h)
     return val;
 }
 
+/* vort_interp(pts) for an (npts, 3) array of (t, x, y) rows (flows.py:409, 631), all host threads */
+void oracle_scalar_eval_many(const spline3_t *s, int linear, const double *pts, int64_t npts, double *out)
+{
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < npts; ++q)
+        out[q] = linear ? oracle_eval_linear3(s, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2])
+                        : oracle_eval_spline3(s, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
+}
+
 /* lavd_grid_2D (diagnostics.py:272-379).  The vorticity interpolant is either the cubic spline
  * (get_callable_scalar, flows.py:387-415) or the trilinear one (get_callable_scalar_linear,
  * flows.py:601-636; used by the reference's own test, tests/test_diagnostics.py:153-173). */

@@ -35,6 +35,17 @@ def lib():
     return _lib.load()
 
 
+@pytest.fixture(scope="session")
+def strict(lib):
+    """Context-manager factory that binds the Python API to libb200cs_strict.so, the parity-
+    calibration build of the same sources (B200CS_STRICT, numbacs_b200/csrc/dop853.cuh): the
+    reference's evaluation order with separately rounded operations and CUDA libm.  Its distance
+    to the oracle is the floor the product build's distance is compared with."""
+    from numbacs_b200 import _build, _lib
+    _build.build_strict()
+    return lambda: _lib.use_library(_lib.STRICT_LIB_PATH)
+
+
 @pytest.fixture
 def coords_dg():
     return np.linspace(0, 2, 21), np.linspace(0, 1, 11)

@@ -14,12 +14,15 @@ with an exact argument reduction gives an exact 0.  Those particles do not move 
 (|dx| ~ 1e-12), so the gates are stated on POSITIONS over all particles, with the step-sequence
 count kept as a bounded diagnostic.
 
-For strongly stretching cases (Bickley jet T = 6, spline fields) even a ONE-ULP change of one
-parameter moves some trajectories of the CPU oracle itself by far more than 1e-8 x L (measured:
-1.4e-5 at Bickley T = 6), because a noisy error estimate (err << 1) feeds the step-size formula.
-There the gate is calibrated in-test: the GPU may differ from the oracle by no more than a small
-multiple of what the oracle differs from itself under a 1-ulp parameter perturbation, and the
-bulk statistics (median, 99th percentile) must still meet 1e-8 x L.
+For strongly stretching cases (Bickley jet T = 6, spline fields) the step sequence of some
+particles is decided by rounding noise (an error estimate err << 1 feeds the step-size formula), so
+no implementation can agree with another beyond that level.  The gate there is calibrated on the
+STRICT build (conftest.py `strict`, csrc/dop853.cuh B200CS_STRICT): the same kernels compiled with
+the reference's evaluation order, separately rounded operations and CUDA libm differ from the
+oracle only by the two libms -- that distance is the measured floor, and the product build may be
+at most 3x the floor on the robust statistics (mismatch count, count above 1e-8 x L, 99th
+percentile) and 10x on the single largest deviation (a heavy-tail statistic), while the bulk
+(median, 99th percentile) must still meet 1e-8 x L.  profiles/r2_parity_floor.json has the numbers.
 """
 import ctypes as C
 
@@ -63,6 +66,7 @@ def compare_flowmaps(gpu, info, ora, steps_o, L):
     d = (np.abs(gpu - ora) / np.asarray(L)).max(axis=-1)
     same = (np.asarray(info["steps"]) == steps_o).all(axis=-1)
     return {"n": d.size, "mismatch": int((~same).sum()), "n_bad": int((d > 1e-8).sum()),
+            "n_bad_match": int((d[same] > 1e-8).sum()),
             "max_match": float(d[same].max()) if same.any() else 0.0,
             "max_all": float(d.max()), "p99": float(np.percentile(d, 99)),
             "median": float(np.median(d))}
@@ -274,20 +278,15 @@ def test_double_gyre_damped(nb, lib, oracle):
         assert np.abs(a - b).max() <= 1e-9
 
 
-def _noise_floor(oracle, flow_o, t0, T, x, y, p, L, k=None, flow_o2=None):
-    """How much the oracle moves under a 1-ulp perturbation (of params[k], or of the coefficient
-    arrays behind flow_o2), over particles whose step counts stay equal."""
-    a, _, _, sa, _ = oracle.flowmap_grid_2D(flow_o, t0, T, x, y, p, full=True)
-    p2 = p.copy()
-    if k is not None:
-        p2[k] = np.nextafter(p2[k], np.inf)
-    b, _, _, sb, _ = oracle.flowmap_grid_2D(flow_o2 or flow_o, t0, T, x, y, p2, full=True)
-    d = (np.abs(a - b) / np.asarray(L)).max(axis=-1)
-    same = (sa == sb).all(axis=-1)
-    return float(d[same].max()), int((~same).sum())
+def assert_within_floor(r, r_strict):
+    """Product-vs-oracle statistics `r` against the strict build's `r_strict` (the floor)."""
+    assert r["mismatch"] <= 3 * max(r_strict["mismatch"], 1), (r, r_strict)
+    assert r["n_bad_match"] <= 3 * max(r_strict["n_bad_match"], 1), (r, r_strict)
+    assert r["p99"] <= max(1e-9, 3 * r_strict["p99"]), (r, r_strict)
+    assert r["max_match"] <= max(1e-8, 10 * r_strict["max_match"]), (r, r_strict)
 
 
-def test_bickley_jet(nb, oracle):
+def test_bickley_jet(nb, oracle, strict):
     """BASELINE config 2 (reduced grid): Bickley jet, forward T = 6 (plot_bickley_ftle.py:24)."""
     f, p, dom = nb.flows.get_predefined_flow("bickley_jet")
     fo, po, _ = oracle.get_predefined_flow("bickley_jet")
@@ -304,11 +303,14 @@ def test_bickley_jet(nb, oracle):
     fm = nb.integration.flowmap_grid_2D(f, 0.0, 6.0, x, y, p, info=info)
     fmo, _, st_o, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 6.0, x, y, po, full=True)
     r = compare_flowmaps(fm, info, fmo, steps_o, L)
-    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 6.0, x, y, po, L, 1)
+    with strict():
+        fs, ps, _ = nb.flows.get_predefined_flow("bickley_jet")
+        info_s = {}
+        fm_s = nb.integration.flowmap_grid_2D(fs, 0.0, 6.0, x, y, ps, info=info_s)
+    r_s = compare_flowmaps(fm_s, info_s, fmo, steps_o, L)
     assert (info["status"] == 1).all()
     assert r["median"] <= 1e-12 and r["p99"] <= 1e-8, r
-    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
-    assert r["mismatch"] <= max(2, 5 * floor_mis), (r, floor_mis)
+    assert_within_floor(r, r_s)
     dx, dy = x[1] - x[0], y[1] - y[0]
     ft = nb.diagnostics.ftle_grid_2D(fm, 6.0, dx, dy)
     fto = oracle.ftle_grid_2D(fmo, 6.0, dx, dy)
@@ -346,7 +348,7 @@ def _dg_like_field(nt=21, nx=41, ny=31):
 
 
 @pytest.mark.parametrize("mode", ["constant", "linear", "nearest"])
-def test_spline_flow(nb, oracle, mode):
+def test_spline_flow(nb, oracle, strict, mode):
     """Cubic-spline velocity (get_interp_arrays_2D -> get_flow_2D -> flowmap_grid_2D), particles
     inside the data grid."""
     t, x, y, U, V = _dg_like_field()
@@ -361,11 +363,13 @@ def test_spline_flow(nb, oracle, mode):
     fm = nb.integration.flowmap_grid_2D(f, 0.0, 8.0, xg, yg, params, info=info)
     fmo, _, _, steps_o, _ = oracle.flowmap_grid_2D(fo, 0.0, 8.0, xg, yg, params, full=True)
     r = compare_flowmaps(fm, info, fmo, steps_o, (2.0, 1.0))
-    fo2 = oracle.get_flow_2D(grid_o, Cuo * (1 + 2.3e-16), Cvo, extrap_mode=mode)
-    floor, floor_mis = _noise_floor(oracle, fo, 0.0, 8.0, xg, yg, params, (2.0, 1.0), flow_o2=fo2)
+    with strict():
+        f_s = nb.flows.get_flow_2D(grid, Cu, Cv, extrap_mode=mode)
+        info_s = {}
+        fm_s = nb.integration.flowmap_grid_2D(f_s, 0.0, 8.0, xg, yg, params, info=info_s)
+    r_s = compare_flowmaps(fm_s, info_s, fmo, steps_o, (2.0, 1.0))
     assert r["median"] <= 1e-12 and r["p99"] <= 1e-9, r
-    assert r["max_match"] <= max(1e-8, 20 * floor), (r, floor)
-    assert r["mismatch"] <= max(1, 5 * floor_mis), (r, floor_mis)
+    assert_within_floor(r, r_s)
     # backward in time with p[0] = -1
     info = {}
     fmb = nb.integration.flowmap_grid_2D(f, 8.0, -6.0, xg, yg, -params, info=info)

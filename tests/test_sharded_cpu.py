@@ -63,6 +63,53 @@ def _worker(rank, world, port, nx, ny, out_path):
     dist.destroy_process_group()
 
 
+def _balanced_worker(rank, world, port, nx, ny, out_path):
+    """flowmap_ftle_sharded + gather_rows on cost-balanced (unequal) row blocks: one block is far
+    larger than ceil(nx / world), the case the equal-size gather used to break on."""
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from numbacs_b200.sharded import balanced_row_blocks, flowmap_ftle_sharded, gather_rows
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    params = np.array([1.0, 0.1, 0.25, 0.0, 0.2 * np.pi, 0.0])
+    cost = np.where(np.arange(nx) < nx // 4, 20.0, 1.0)      # the first quarter is 20x as expensive
+    blocks = balanced_row_blocks(cost, world)
+    sizes = [b - a for a, b in blocks]
+    assert max(sizes) > -(-nx // world) and min(sizes) >= 1, blocks
+    fm, ft, (i0, i1) = flowmap_ftle_sharded(0, 0.0, 5.0, x, y, params, x[1] - x[0], y[1] - y[0],
+                                            backend=_oracle_backend(), blocks=blocks)
+    assert (i0, i1) == blocks[rank]
+    fm_all = gather_rows(fm.contiguous(), nx, blocks=blocks)
+    pre = torch.full((nx, ny), -1.0, dtype=torch.float64) if rank == 0 else None
+    ft_all = gather_rows(ft, nx, blocks=blocks, out=pre)
+    if rank == 0:
+        assert ft_all is pre
+        np.savez(out_path, fm=fm_all.numpy(), ft=ft_all.numpy())
+    else:
+        assert fm_all is None and ft_all is None
+    # a block list that does not match what the rank holds is an error on every rank, not a hang
+    with pytest.raises(ValueError):
+        gather_rows(ft, nx, blocks=[(0, nx)] + [(nx, nx)] * (world - 1) if i1 - i0 != nx else [(0, 1)] * world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gather_rows_balanced_blocks_gloo(world, tmp_path):
+    import torch.multiprocessing as mp
+    import oracle as O
+    nx, ny = 26, 9
+    out = str(tmp_path / "bal.npz")
+    mp.spawn(_balanced_worker, args=(world, _free_port(), nx, ny, out), nprocs=world, join=True)
+    got = np.load(out)
+    x, y = np.linspace(0, 2, nx), np.linspace(0, 1, ny)
+    f, p, _ = O.get_predefined_flow("double_gyre")
+    fm = O.flowmap_grid_2D(f, 0.0, 5.0, x, y, p)
+    assert np.array_equal(got["fm"], fm)
+    assert np.array_equal(got["ft"], O.ftle_grid_2D(fm, 5.0, x[1] - x[0], y[1] - y[0]))
+
+
 def _oracle_ridge_backend():
     import torch
     import oracle as O
@@ -225,5 +272,14 @@ def test_balanced_row_blocks():
     # uniform cost -> (almost) equal sizes; degenerate inputs stay valid
     sizes = [b - a for a, b in balanced_row_blocks(np.ones(1000), 8)]
     assert max(sizes) - min(sizes) <= 1
-    assert balanced_row_blocks(np.ones(2), 4)[-1][1] == 2
+    # fewer rows than ranks: the equal-size partition (empty blocks only at the end, never between)
+    assert balanced_row_blocks(np.ones(2), 4) == [(0, 1), (1, 2), (2, 2), (2, 2)]
     assert balanced_row_blocks(np.zeros(0), 3) == [(0, 0)] * 3
+    # a cost concentrated in a few rows must not starve any rank of rows
+    spike = np.ones(64)
+    spike[:2] = 1e6
+    for min_rows in (1, 2):
+        blocks = balanced_row_blocks(spike, 8, min_rows=min_rows)
+        assert blocks[0][0] == 0 and blocks[-1][1] == 64
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(7))
+        assert min(b - a for a, b in blocks) >= min_rows, blocks
