@@ -15,7 +15,9 @@ A step = one full flow map + FTLE pass.
   value : device-timed (CUDA events on the launching stream, barrier + synchronize on both sides,
           max over ranks), x / y already resident in HBM.
   e2e   : the same pass through the public API with HOST buffers: x, y copied host->device from
-          pinned memory every step, the FTLE block copied device->host into pinned memory.
+          pinned memory every step, the flow map AND the FTLE field copied device->host (24 B/point)
+          into one host buffer per field that all ranks share, so rank 0 holds the assembled arrays;
+          at N > 1 the planning pass (cost-balanced row cuts) runs inside every step.
   roofline : the integration kernel (FP64-FMA bound; neither HBM nor tensor), ALGORITHMIC flops
           F = N_att*346 + N_fev*35 + 40 per particle from the kernel's own step
           statistics, divided by the kernel time measured live with CUDA events; peak = FP64 DFMA
@@ -554,6 +556,28 @@ def run_b200(args):
         except Exception:
             ftle_traffic = None
         ftle_gbs = 24.0 * pts / world / (ft_ms * 1e-3) / 1e9
+        # end to end = what flowmap_grid_2D + ftle_grid_2D hand back to the caller: the [n, n, 2] flow map
+        # AND the [n, n] FTLE field in host memory (24 B/point over PCIe); the FTLE-only variant
+        # (flow map left in HBM) is reported beside it
+        h2d = int(8 * (n + 2 * (world - 1) + n * world))
+        how = ("one b200cs_flowmap_ftle_grid_2d call per rank and step, host pointers only: x/y from pinned "
+               "memory, flow-map and FTLE rows into ONE host buffer per field shared by all ranks (POSIX shared "
+               "memory registered with CUDA in every process), so rank 0 holds the assembled arrays when the "
+               "step ends; downloads overlap the integration of later row chunks; the per-step planning pass "
+               "(cost-balanced cuts) is inside the timed region")
+        ftle_only = {"value": e2e_val, "ms_per_step": e2e_ms / K, "d2h_bytes_per_step": int(8 * pts),
+                     "note": "flowmap_out = NULL: only the FTLE field leaves the GPU"}
+        if e2e_fm_ms is not None:
+            e2e_entry = {"value": pts / (e2e_fm_ms / K * 1e-3), "unit": "grid points/s", "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": int(24 * pts), "ms_per_step": e2e_fm_ms / K,
+                         "assembled_on_rank0_host": True, "planning_inside": world > 1, "result": how,
+                         "ftle_only": ftle_only}
+        else:
+            e2e_entry = {"value": e2e_val, "unit": "grid points/s", "h2d_bytes_per_step": h2d,
+                         "d2h_bytes_per_step": int(8 * pts), "ms_per_step": e2e_ms / K,
+                         "assembled_on_rank0_host": False, "planning_inside": world > 1,
+                         "result": how + " [no shared memory on this box: every rank kept its FTLE rows in its own "
+                                         "pinned buffer and the flow map stayed in HBM]"}
         line = {
             "metric": "FTLE grid points/s (flowmap+FTLE)", "value": value, "unit": "grid points/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -567,21 +591,7 @@ def run_b200(args):
                        "row_blocks": [list(b) for b in blocks],
                        "l2": "no flush: every step rewrites 24 B/point of outputs "
                              f"({24 * pts / world / 1e9:.2f} GB per GPU >> 126 MB L2), inputs are 2 x {n} doubles"},
-            "e2e": {"value": e2e_val, "unit": "grid points/s",
-                    "h2d_bytes_per_step": int(8 * (n + 2 * (world - 1) + n * world)),
-                    "d2h_bytes_per_step": int(8 * pts), "ms_per_step": e2e_ms / K,
-                    "assembled_on_rank0_host": bool(assembled or world == 1),
-                    "planning_inside": world > 1,
-                    "result": "one b200cs_flowmap_ftle_grid_2d call per rank and step, host pointers only: x/y "
-                              "from pinned memory, FTLE rows into ONE host buffer shared by all ranks (POSIX "
-                              "shared memory registered with CUDA in every process), so rank 0 holds the "
-                              "assembled field when the step ends; downloads overlap the integration of later "
-                              "row chunks; the per-step planning pass (cost-balanced cuts) is inside",
-                    "with_flowmap": None if e2e_fm_ms is None else {
-                        "value": pts / (e2e_fm_ms / K * 1e-3), "ms_per_step": e2e_fm_ms / K,
-                        "d2h_bytes_per_step": int(24 * pts),
-                        "note": "the same call with flowmap_out set: the [n, n, 2] flow map that the reference's "
-                                "flowmap_grid_2D returns is downloaded too (16 B/point more over PCIe)"}},
+            "e2e": e2e_entry,
             "gpu_launches": 2 * K * world,  # timed (device) region: flow-map + FTLE kernel per step and rank
             "roofline": {"bound": "fp64", "achieved": fm_tflops_per_gpu, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": fm_tflops_per_gpu / fp64_peak, "traffic": traffic,
@@ -649,13 +659,14 @@ def parity_block(args, n, world, rank, blocks, slab, own, ftle, HW, has_lo, f, p
         if rank == 0:
             hi_fm = torch.empty((b - cut, n, 2), dtype=torch.float64, device="cuda")
             hi_ft = torch.empty((b - cut, n), dtype=torch.float64, device="cuda")
-            dist.recv(hi_fm, src=1)
-            dist.recv(hi_ft, src=1)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.irecv, hi_fm, 1), dist.P2POp(dist.irecv, hi_ft, 1)]):
+                req.wait()
             gpu_fm = torch.cat([own[a:cut], hi_fm])
             gpu_ft = torch.cat([ftle[a:cut], hi_ft])
         elif rank == 1:
-            dist.send(own[:b - cut].contiguous(), dst=0)
-            dist.send(ftle[:b - cut].contiguous(), dst=0)
+            for req in dist.batch_isend_irecv([dist.P2POp(dist.isend, own[:b - cut].contiguous(), 0),
+                                               dist.P2POp(dist.isend, ftle[:b - cut].contiguous(), 0)]):
+                req.wait()
     parity = cpu = None
     if rank == 0:
         reps = 3 if world == 1 else 1
