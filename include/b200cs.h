@@ -289,6 +289,29 @@ B200CS_API int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, 
                        int64_t *roots_compact /*[capacity]*/, int64_t capacity, int64_t *count,
                        void *stream);
 
+/* _linked_ridge_pts(f, eigvec_max, x, y, sdd_thresh, percentile, c)   (ridges.py:418-603, with
+ * _link_points_stepper 321-415).  HOST code (a serial greedy walk): r_pts [nx*ny,3], r_vec
+ * [nx*ny,2], sdd [nx*ny] are the host copies of b200cs_ftle_ridge_pts' per-pixel outputs, h =
+ * min(dx, dy).  Outputs: linked [n_pts,2] (ordered points, grouped by curve), ridge_len
+ * [n_curves,2] = (index one past the curve's last point, its length), endpoints [2 n_curves,3]
+ * (x, y, label: +k for the first point of curve k, -(k + 0.1) for the last), ep_tanvecs
+ * [2 n_curves,2].  counts[0..1] = (n_pts, n_curves) always; nothing is written when a capacity is
+ * too small (call again with room). */
+B200CS_API int b200cs_link_ridge_pts(const double *r_pts, const double *r_vec, const double *sdd, int64_t nx,
+                          int64_t ny, double h, double c, double sdd_thresh, double *linked,
+                          int64_t linked_capacity, int32_t *ridge_len, double *endpoints,
+                          double *ep_tanvecs, int64_t curve_capacity, int64_t *counts);
+
+/* ftle_ordered_ridges(f, eigvec_max, x, y, dist_tol, ep_tan_ang, min_ridge_pts, ...)   (ridges.py:720-1054,
+ * with _endpoint_distances 606-642 and _connect_endpoints 645-717): joins the curves of
+ * b200cs_link_ridge_pts whose end points are within dist_tol and line up within ep_tan_ang.  HOST
+ * code.  out_pts [<= n_pts, 2] holds the resulting ridges back to back, offsets [n_out + 1] their
+ * boundaries (offsets needs room for n_curves + 1 entries). */
+B200CS_API int b200cs_order_ridges(const double *linked, int64_t n_pts, const int32_t *ridge_len,
+                        const double *endpoints, const double *ep_tanvecs, int64_t n_curves,
+                        double dist_tol, double ep_tan_ang, int64_t min_ridge_pts, double *out_pts,
+                        int64_t *offsets, int64_t *n_out);
+
 /* flowmap_composition(flowmaps, grid, nT)      (integration.py:609-644)
  * flowmaps is [nT, nx, ny, 2] (the flow maps over [t0 + k h, t0 + (k+1) h]), grid6 =
  * {x0, x1, nx, y0, y1, ny} (the UCGrid tuple, host or device); composed [nx, ny, 2] =

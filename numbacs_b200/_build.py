@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libb200cs.so")
 
 SOURCES = ["capi.cu", "flowmap_dispatch.cu", "flowmap_dg.cu", "flowmap_dg_damped.cu", "flowmap_bickley.cu",
            "flowmap_abc.cu", "flowmap_spline.cu", "flowmap_linear.cu", "ftle_kernels.cu", "diag_kernels.cu",
-           "tensor_kernels.cu"]
+           "tensor_kernels.cu", "ridge_link.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
 

@@ -61,6 +61,8 @@ PROTOTYPES = {
                               _vp, _i64, _vp, _vp],
     "b200cs_ftle_ridges": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _i64, _vp,
                            _vp],
+    "b200cs_link_ridge_pts": [_vp, _vp, _vp, _i64, _i64, _d, _d, _d, _vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    "b200cs_order_ridges": [_vp, _i64, _vp, _vp, _vp, _i64, _d, _d, _i64, _vp, _vp, _vp],
     "b200cs_flowmap_composition": [_vp, _vp, _i64, _vp, _vp],
     "b200cs_binary_mask_dilation": [_vp, _i64, _i64, _i, _vp, _vp],
     "b200cs_flowmap_composition_series": [_vp, _vp, _i64, _i64, _vp, _vp],

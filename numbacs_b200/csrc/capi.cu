@@ -3,6 +3,21 @@
 #include "common.cuh"
 #include "launch.cuh"
 
+#include <cstring>
+#include <vector>
+
+namespace b200cs {
+// ridge_link.cu (host code)
+void link_ridge_points(const double *r_pts_in, const double *r_vec, const double *sdd, long long nx, long long ny,
+                       double h, double c, double sdd_thresh, std::vector<double> &linked,
+                       std::vector<int32_t> &ridge_len, std::vector<double> &endpoints,
+                       std::vector<double> &tanvecs);
+void order_ridges(const std::vector<double> &linked, const std::vector<int32_t> &ridge_len,
+                  const std::vector<double> &endpoints, const std::vector<double> &tanvecs, double dist_tol,
+                  double ep_tan_ang, long long min_ridge_pts, std::vector<double> &out_pts,
+                  std::vector<long long> &offsets);
+}  // namespace b200cs
+
 namespace b200cs {
 
 // ---------------------------------------------------------------- errors
@@ -982,6 +997,58 @@ int b200cs_ftle_ridges(const double *ftle, const double *eigvec_max, int64_t ev_
                 B2_CHECK_CUDA(cudaStreamSynchronize(s));
             }
         }
+    });
+}
+
+int b200cs_link_ridge_pts(const double *r_pts, const double *r_vec, const double *sdd, int64_t nx, int64_t ny,
+                          double h, double c, double sdd_thresh, double *linked, int64_t linked_capacity,
+                          int32_t *ridge_len, double *endpoints, double *ep_tanvecs, int64_t curve_capacity,
+                          int64_t *counts) {
+    return guarded([&] {
+        B2_REQUIRE(r_pts && r_vec && sdd && counts, "null argument");
+        B2_REQUIRE(nx >= 5 && ny >= 5, "the grid needs at least 5 points per axis (ridge points live on [2, n-2))");
+        B2_REQUIRE(h > 0.0, "h must be positive");
+        B2_REQUIRE(!is_device_ptr(r_pts) && !is_device_ptr(r_vec) && !is_device_ptr(sdd),
+                   "the linking stage is host code: pass host arrays (download r_pts / r_vec / sdd first)");
+        std::vector<double> lk, ep, tv;
+        std::vector<int32_t> rl;
+        link_ridge_points(r_pts, r_vec, sdd, nx, ny, h, c, sdd_thresh, lk, rl, ep, tv);
+        const int64_t n_pts = (int64_t)lk.size() / 2, n_curves = (int64_t)rl.size() / 2;
+        counts[0] = n_pts;
+        counts[1] = n_curves;
+        if (n_pts > linked_capacity || n_curves > curve_capacity) return;   // sizes only: call again with room
+        B2_REQUIRE((n_pts == 0 || linked) && (n_curves == 0 || (ridge_len && endpoints && ep_tanvecs)),
+                   "null output buffer");
+        if (n_pts) std::memcpy(linked, lk.data(), lk.size() * sizeof(double));
+        if (n_curves) {
+            std::memcpy(ridge_len, rl.data(), rl.size() * sizeof(int32_t));
+            std::memcpy(endpoints, ep.data(), ep.size() * sizeof(double));
+            std::memcpy(ep_tanvecs, tv.data(), tv.size() * sizeof(double));
+        }
+    });
+}
+
+int b200cs_order_ridges(const double *linked, int64_t n_pts, const int32_t *ridge_len, const double *endpoints,
+                        const double *ep_tanvecs, int64_t n_curves, double dist_tol, double ep_tan_ang,
+                        int64_t min_ridge_pts, double *out_pts, int64_t *offsets, int64_t *n_out) {
+    return guarded([&] {
+        B2_REQUIRE(n_out && n_pts >= 0 && n_curves >= 0, "bad argument");
+        *n_out = 0;
+        if (n_curves == 0) return;
+        B2_REQUIRE(linked && ridge_len && endpoints && ep_tanvecs && out_pts && offsets, "null argument");
+        for (int64_t r = 0; r < n_curves; ++r)
+            B2_REQUIRE(ridge_len[2 * r + 1] >= 2 && ridge_len[2 * r] >= ridge_len[2 * r + 1] && ridge_len[2 * r] <= n_pts,
+                       "ridge_len[%lld] = (%d, %d) does not index linked[%lld]", (long long)r, ridge_len[2 * r],
+                       ridge_len[2 * r + 1], (long long)n_pts);
+        std::vector<double> lk(linked, linked + 2 * n_pts), ep(endpoints, endpoints + 6 * n_curves),
+            tv(ep_tanvecs, ep_tanvecs + 4 * n_curves), out;
+        std::vector<int32_t> rl(ridge_len, ridge_len + 2 * n_curves);
+        std::vector<long long> offs;
+        order_ridges(lk, rl, ep, tv, dist_tol, ep_tan_ang, min_ridge_pts, out, offs);
+        // every curve is used at most once, so out never exceeds n_pts points / n_curves curves
+        *n_out = (int64_t)offs.size() - 1;
+        if (!out.empty()) std::memcpy(out_pts, out.data(), out.size() * sizeof(double));
+        for (size_t k = 0; k < offs.size(); ++k) offsets[k] = offs[k];
     });
 }
 

@@ -51,11 +51,17 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
 #ifndef B200CS_BICKLEY_MINBLOCKS
 #define B200CS_BICKLEY_MINBLOCKS 5
 #endif
+#ifndef B200CS_BICKLEY_THREADS
+#define B200CS_BICKLEY_THREADS 128
+#endif
+#ifndef B200CS_BICKLEY_LOCKSTEP
+#define B200CS_BICKLEY_LOCKSTEP false
+#endif
 template <>
 struct KernelShape<BickleyJet, false> {
-    static constexpr int kThreads = 128;
+    static constexpr int kThreads = B200CS_BICKLEY_THREADS;
     static constexpr int kMinBlocks = B200CS_BICKLEY_MINBLOCKS;
-    static constexpr bool kLockstep = false;
+    static constexpr bool kLockstep = B200CS_BICKLEY_LOCKSTEP;
 };
 #ifndef B200CS_SPLINE_THREADS
 #define B200CS_SPLINE_THREADS 512

@@ -40,6 +40,9 @@ struct RhsParams {
 #ifndef B200CS_ABC_WIDE
 #define B200CS_ABC_WIDE 1
 #endif
+#ifndef B200CS_BICKLEY_NOINLINE
+#define B200CS_BICKLEY_NOINLINE 0
+#endif
 #ifndef B200CS_LEAN_F
 #define B200CS_LEAN_F 1
 #endif
@@ -186,7 +189,29 @@ struct BickleyJet {
     __device__ __forceinline__ explicit BickleyJet(const RhsParams &P_) : P(P_) {}
     template <int M>
     __device__ __forceinline__ void time_part(const double (&)[M], double (&)[M]) const {}
+#if B200CS_BICKLEY_NOINLINE
+    // The RHS is ~250 instructions; inlined into the 12 stages + FSAL + hinit it makes the attempt
+    // loop 53 KB, well above the 32 KB instruction cache (ncu: no_instruction 2.4 cycles per issue).
+    // Out of line it is ONE copy that every stage calls: the loop drops below the cache size and the
+    // call costs ~5 % of the body.
+    static __device__ __noinline__ double2 eval_ool(const RhsParams *Pp, double t, double y0, double y1) {
+        const BickleyJet self(*Pp);
+        const double y[2] = {y0, y1};
+        double dy[2];
+        self.eval_body(t, y, dy);
+        return make_double2(dy[0], dy[1]);
+    }
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
+        const double2 r = eval_ool(&P, t, y[0], y[1]);
+        dy[0] = r.x;
+        dy[1] = r.y;
+    }
+#else
+    __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
+        eval_body(t, y, dy);
+    }
+#endif
+    __device__ __forceinline__ void eval_body(double t, const double (&y)[2], double (&dy)[2]) const {
         const double *p = P.p;
         const double tt = p[0] * t;
 #if B200CS_STRICT_RHS

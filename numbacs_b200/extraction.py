@@ -13,17 +13,19 @@ labels ridge_bool with scipy.ndimage.label and gathers each label with a full-gr
 here a union-find kernel labels the ridge pixels on the device and only the (few) ridge points
 are grouped on the host.
 
-The serial greedy linking of ridge points into ORDERED curves (ftle_ordered_ridges,
-ridges.py:418-1054) is host-side geometry and is not part of this package.
+The serial greedy linking of ridge points into ORDERED curves (_linked_ridge_pts ridges.py:418-603,
+ftle_ordered_ridges 720-1054) is inherently sequential; it runs on the host in native code
+(csrc/ridge_link.cu, b200cs_link_ridge_pts / b200cs_order_ridges) on the per-pixel arrays the
+device kernel behind _ftle_ridge_pts_connect produced.
 """
 import ctypes as C
-from math import floor
+from math import floor, pi
 
 import numpy as np
 
 from . import _lib
 
-__all__ = ["ftle_ridge_pts", "ftle_ridges", "percentile_value"]
+__all__ = ["ftle_ridge_pts", "ftle_ridges", "ftle_ordered_ridges", "percentile_value"]
 
 
 def percentile_value(f, percentile):
@@ -156,3 +158,58 @@ def ftle_ridges(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, min_ridge_pts
     cuts = np.flatnonzero(np.diff(sroots)) + 1
     groups = np.split(order, cuts) if n else []
     return [pts[g] for g in groups if len(g) >= min_ridge_pts]
+
+
+def _host(a):
+    return np.ascontiguousarray(a.cpu().numpy() if _lib._is_torch(a) else a, dtype=np.float64)
+
+
+def _linked_ridge_pts(f, eigvec_max, x, y, sdd_thresh=0.0, percentile=0, c=1.0):
+    """Ridge points ordered and grouped into curves (extraction/ridges.py:418-603) ->
+    (linked_ridges_arr (n, 2), ridge_len (k, 2) int32, endpoints (2k, 3), ep_tanvecs (2k, 2)).
+
+    The per-pixel ridge test runs on the GPU (_ftle_ridge_pts_connect); the greedy walk over its
+    output is serial and runs on the host (b200cs_link_ridge_pts)."""
+    r_pts, r_vec, sdd, h = _ftle_ridge_pts_connect(f, eigvec_max, x, y, sdd_thresh, percentile)
+    fa = _lib.arg_in(f)
+    nx, ny = int(fa.obj.shape[0]), int(fa.obj.shape[1])
+    r_pts, r_vec, sdd = _host(r_pts), _host(r_vec), _host(sdd)
+    cap = int(np.count_nonzero(sdd < 0.0))
+    ccap = cap // 2 + 1
+    linked = np.empty((max(cap, 1), 2), np.float64)
+    ridge_len = np.empty((ccap, 2), np.int32)
+    endpoints = np.empty((2 * ccap, 3), np.float64)
+    tanvecs = np.empty((2 * ccap, 2), np.float64)
+    counts = np.zeros(2, np.int64)
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(_lib.load().b200cs_link_ridge_pts(vp(r_pts), vp(r_vec), vp(sdd), nx, ny, float(h), float(c),
+                                                 float(sdd_thresh), vp(linked), cap, vp(ridge_len), vp(endpoints),
+                                                 vp(tanvecs), ccap, vp(counts)))
+    n, k = int(counts[0]), int(counts[1])
+    if n > cap or k > ccap:
+        raise RuntimeError("ridge linking produced more points than there are ridge pixels")
+    return linked[:n], ridge_len[:k], endpoints[:2 * k], tanvecs[:2 * k]
+
+
+def ftle_ordered_ridges(f, eigvec_max, x, y, dist_tol, ep_tan_ang=pi / 4, min_ridge_pts=5, sdd_thresh=0.0,
+                        percentile=0, c=1.0):
+    """Ordered, connected FTLE ridges -> list of (k_i, 2) arrays (extraction/ridges.py:720-1054).
+
+    Ridge points are linked into curves (_linked_ridge_pts); curves whose end points are within
+    dist_tol of each other, with both curve tangents within ep_tan_ang of the connecting segment,
+    are joined; results shorter than min_ridge_pts are dropped."""
+    linked, ridge_len, endpoints, tanvecs = _linked_ridge_pts(f, eigvec_max, x, y, sdd_thresh, percentile, c)
+    k = len(ridge_len)
+    if k == 0:
+        return []
+    out = np.empty((max(len(linked), 1), 2), np.float64)
+    offsets = np.zeros(k + 1, np.int64)
+    n_out = np.zeros(1, np.int64)
+    linked = np.ascontiguousarray(linked)
+    ridge_len, endpoints, tanvecs = (np.ascontiguousarray(a) for a in (ridge_len, endpoints, tanvecs))
+    vp = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(_lib.load().b200cs_order_ridges(vp(linked), len(linked), vp(ridge_len), vp(endpoints), vp(tanvecs), k,
+                                               float(dist_tol), float(ep_tan_ang), int(min_ridge_pts), vp(out),
+                                               vp(offsets), vp(n_out)))
+    m = int(n_out[0])
+    return [out[int(offsets[r]):int(offsets[r + 1])].copy() for r in range(m)]

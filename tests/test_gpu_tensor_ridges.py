@@ -465,3 +465,72 @@ def test_flowmap_composition_series_equals_initial_plus_steps(nb):
     xd, yd = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
     sd = I.flowmap_composition_series(f, t0, T, h, n, xd, yd, grid, p)
     assert sd.is_cuda and np.array_equal(sd.cpu().numpy(), series)
+
+
+# ------------------------------------------------------------------ ordered ridges (section 8(f)1)
+
+@pytest.mark.parametrize("tag", ["ref", "dg_a", "dg_b", "dg_c", "rnd_a", "rnd_b", "rnd_c"])
+def test_ftle_ordered_ridges_match_the_real_reference(nb, tag):
+    """ftle_ordered_ridges end to end (per-pixel ridge test on the GPU, linking + end-point matching in
+    the library's host code) against frozen outputs of the real reference functions
+    (tests/golden/make_ordered_ridges_golden.py) and, for `ref`, the reference's own pickled golden
+    (tests/test_extraction.py:23-29)."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ordered_ridges_golden.npz"))
+    dist_tol, ang, mrp, thr, pct, c, h = G[tag + "_args"]
+    f, ev, x, y = (G[f"{tag}_{k}"] for k in ("f", "ev", "x", "y"))
+    lk, rl, ep, tv = nb.extraction._linked_ridge_pts(f, ev, x, y, sdd_thresh=thr, percentile=int(pct), c=c)
+    assert np.array_equal(rl, G[tag + "_ridge_len"]) and np.array_equal(lk, G[tag + "_linked"])
+    assert np.array_equal(ep, G[tag + "_endpoints"]) and np.allclose(tv, G[tag + "_tanvecs"], rtol=0, atol=1e-15)
+    ridges = nb.extraction.ftle_ordered_ridges(f, ev, x, y, dist_tol, ep_tan_ang=ang, min_ridge_pts=int(mrp),
+                                               sdd_thresh=thr, percentile=int(pct), c=c)
+    assert [len(r) for r in ridges] == list(G[tag + "_ordered_len"])
+    assert np.array_equal(np.concatenate(ridges) if ridges else np.zeros((0, 2)), G[tag + "_ordered_cat"])
+    if tag == "ref":
+        assert [len(r) for r in ridges] == list(G["ref_pkl_ordered_len"])
+        assert np.allclose(np.concatenate(ridges), G["ref_pkl_ordered_cat"])
+
+
+def test_dg_ftle_ridges_example_runs_as_numbacs(nb, oracle):
+    """examples/ftle/plot_dg_ftle_ridges.py:13-72 of the reference, its compute lines verbatim
+    (imports through the `numbacs` alias, matplotlib left out), on the GPU path; the ridges are
+    compared with the same pipeline fed by the CPU oracle's flow map."""
+    nb.install_as_numbacs()
+    from math import copysign
+    from numbacs.flows import get_predefined_flow
+    from numbacs.integration import flowmap_grid_2D
+    from numbacs.diagnostics import ftle_from_eig, C_eig_2D
+    from numbacs.extraction import ftle_ordered_ridges
+    t0 = 0.0
+    T = -10.0
+    int_direction = copysign(1, T)
+    funcptr, params, domain = get_predefined_flow("double_gyre", int_direction=int_direction)
+    nx, ny = 401, 201
+    x = np.linspace(domain[0][0], domain[0][1], nx)
+    y = np.linspace(domain[1][0], domain[1][1], ny)
+    dx = x[1] - x[0]
+    dy = y[1] - y[0]
+    flowmap = flowmap_grid_2D(funcptr, t0, T, x, y, params)
+    eigvals, eigvecs = C_eig_2D(flowmap, dx, dy)
+    eigval_max = eigvals[:, :, 1]
+    eigvec_max = eigvecs[:, :, :, 1]
+    ftle = ftle_from_eig(eigval_max, T)
+    percentile = 0
+    sdd_thresh = 10.0
+    dist_tol = 5e-2
+    ridge_curves = ftle_ordered_ridges(
+        ftle, eigvec_max, x, y, dist_tol, percentile=percentile, sdd_thresh=sdd_thresh
+    )
+    assert len(ridge_curves) > 10 and all(r.ndim == 2 and r.shape[1] == 2 and len(r) >= 5 for r in ridge_curves)
+    assert max(len(r) for r in ridge_curves) > 300           # the main ridge is one long ordered curve
+    # the same tail on the oracle's flow map
+    fo, po, _ = oracle.get_predefined_flow("double_gyre", int_direction=int_direction)
+    fmo = oracle.flowmap_grid_2D(fo, t0, T, x, y, po)
+    vo, eo = C_eig_2D(fmo, dx, dy)
+    ref_curves = ftle_ordered_ridges(ftle_from_eig(vo[:, :, 1], T), eo[:, :, :, 1], x, y, dist_tol,
+                                     percentile=percentile, sdd_thresh=sdd_thresh)
+    n_gpu, n_ref = sum(len(r) for r in ridge_curves), sum(len(r) for r in ref_curves)
+    print("ordered ridges gpu/oracle:", len(ridge_curves), len(ref_curves), "points", n_gpu, n_ref)
+    assert abs(n_gpu - n_ref) <= 0.01 * n_ref and abs(len(ridge_curves) - len(ref_curves)) <= 2
+    if [len(r) for r in ridge_curves] == [len(r) for r in ref_curves]:
+        assert np.abs(np.concatenate(ridge_curves) - np.concatenate(ref_curves)).max() <= 1e-6
