@@ -60,6 +60,16 @@
 #ifndef B200CS_LEAN2
 #define B200CS_LEAN2 B200CS_LEAN
 #endif
+// B200CS_CTRL_FAST (round 2): the step-size controller without IEEE divisions -- 1/sk from the MUFU
+// reciprocal seed + two Newton steps, and h_new = h * min(6, max(1/3, 0.9 err^(-1/8))) with
+// err^(-1/8) from three MUFU rsqrt seeds + two Newton steps (~1e-16 relative), instead of
+// pow_eighth + division by 0.9 + division of h by the factor.  Parity: the integrator-only /
+// RHS-only decomposition (profiles/r2_parity_decomp.json) shows that ulp-level changes of the
+// controller leave the distance to the oracle unchanged; the accept / reject test itself
+// (err <= 1) is not touched.
+#ifndef B200CS_CTRL_FAST
+#define B200CS_CTRL_FAST (!B200CS_STRICT_INT)
+#endif
 #ifndef B200CS_SYNC_EVERY
 #define B200CS_SYNC_EVERY 8
 #endif
@@ -107,6 +117,31 @@ __device__ __forceinline__ double pow_eighth(double x) { return sqrt_fast(sqrt_f
 __device__ __forceinline__ double pow_eighth(double x) { return pow(x, 0.125); }  // libm pow, as the reference
 #else
 __device__ __forceinline__ double pow_eighth(double x) { return sqrt(sqrt(sqrt(x))); }
+#endif
+#if B200CS_CTRL_FAST
+// 1/x for a normal positive x: MUFU.RCP64H seed (~2^-22) and two Newton steps
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(r, fma(-x, r, 1.0), r);
+    return fma(r, fma(-x, r, 1.0), r);
+}
+// x^(-1/8) for x > 0: z0 from three chained MUFU.RSQ64H seeds (x^-1/2 -> x^-1/4 -> x^-1/8, ~1e-6),
+// then Newton on z^-8 = x:  z <- z + z (1 - x z^8) / 8   (quadratic, two steps -> rounding level)
+__device__ __forceinline__ double inv_eighth_root(double x) {
+    double s1, s2, z;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s1) : "d"(x));
+    const double t1 = x * s1;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s2) : "d"(t1));
+    const double t2 = t1 * s2;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(t2));
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+        z = fma(z * fma(-x, z8, 1.0), 0.125, z);
+    }
+    return z;
+}
 #endif
 // a / c for a compile-time constant c: q = a*rc, one FMA residual correction -> the correctly
 // rounded quotient in 3 FP64 instructions (see tensor_kernels.cu, div_const)
@@ -297,7 +332,10 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             double e3 = detail::mad(-dop::kTab.bhh[0], K[1][i], s);
             e3 = detail::mad(-dop::kTab.bhh[1], K[9][i], e3);
             e3 = detail::mad(-dop::kTab.bhh[2], K[12][i], e3);
-#if B200CS_LEAN
+#if B200CS_CTRL_FAST
+            const double rsk = detail::rcp_fast(sk);  // sk = atol + rtol |y| is a normal positive number
+            e3 *= rsk;
+#elif B200CS_LEAN
             const double rsk = 1.0 / sk;  // one reciprocal serves both estimates (<= 1 ulp from e/sk)
             e3 *= rsk;
 #else
@@ -312,7 +350,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             e5 = detail::mad(dop::kTab.er[10], K[10][i], e5);
             e5 = detail::mad(dop::kTab.er[11], K[11][i], e5);
             e5 = detail::mad(dop::kTab.er[12], K[12][i], e5);
-#if B200CS_LEAN
+#if B200CS_LEAN || B200CS_CTRL_FAST
             e5 *= rsk;
 #else
             e5 /= sk;
@@ -326,6 +364,13 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
 #else
         err = fabs(h) * err * sqrt(1.0 / (deno * (double)N));
 #endif
+#if B200CS_CTRL_FAST
+        // g = 0.9 err^(-1/8) = 1 / (fac11 / safe); err == 0 (or below the seed's range) -> +inf, i.e. the
+        // growth clamp; a NaN err stays NaN and fmax / fmin then pick the 1/3 of a rejected step
+        double g = kSafe * detail::inv_eighth_root(err);
+        if (err <= 1.0e-280) g = __longlong_as_double(0x7ff0000000000000LL);
+        double hnew = h * fmin(1.0 / kFacc2, fmax(1.0 / kFacc1, g));
+#else
         const double fac11 = detail::pow_eighth(err);
 #if B200CS_LEAN2
         const double fac11s = detail::div_const(fac11, kSafe, 1.0 / kSafe);
@@ -334,6 +379,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
 #endif
         const double fac = fmax(kFacc2, fmin(kFacc1, fac11s));  // beta = 0
         double hnew = h / fac;
+#endif
         if (err <= 1.0) {
             // ---- accepted
             ++cnt.accepted;
@@ -394,7 +440,11 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             reject = false;
         } else {
             // ---- rejected
+#if B200CS_CTRL_FAST
+            hnew = h * fmax(1.0 / kFacc1, g);
+#else
             hnew = h / fmin(kFacc1, fac11s);
+#endif
             reject = true;
             last = false;
             ++cnt.rejected;

@@ -193,6 +193,12 @@ static __constant__ WideTrigConsts kWide = {
     {-0.5, 0.04166666666666634, -0.0013888888888860694, 2.4801587292441663e-05,
      -2.755731776674132e-07, 2.08766308298722e-09, -1.1464688686901012e-11, 4.6276610380051693e-14}};
 
+// host-visible copy of kWide.cp (capi.cu folds the double gyre's eps into it; the CPU test
+// tests/test_trig_poly_cpu.py checks that the two tables are the same numbers)
+constexpr double kSinPiCpHost[8] = {
+    -5.16771278004997, 2.55016403987734, -0.599264529320343, 0.08214588659675232,
+    -0.007370430719634586, 0.00046630087411496363, -2.1906201655131958e-05, 7.725743030789876e-07};
+
 // s[m] = sin(pi u[m]), wide kernel
 template <int M>
 __device__ __forceinline__ void sinpi_wide_v(const double (&u)[M], double (&s)[M]) {
@@ -265,6 +271,39 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
         for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
 #pragma unroll
     for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], kWide.pi_hi), q[m] & 1);
+}
+
+// amp * sin(pi u) with the amplitude folded into the coefficients: ce = amp * {cp0 .. cp7, pi}
+// (formed once per launch on the host).  Same reduction and Horner chain as sinpi12_v; the folded
+// coefficients carry one extra rounding each (<= 1 ulp of a coefficient, i.e. the same size as
+// the rounding of the product amp * sin it replaces).
+template <int M>
+__device__ __forceinline__ void sinpi12_scaled_v(const double (&u)[M], double (&s)[M], const double (&ce)[9]) {
+    bool slow = false;
+#pragma unroll
+    for (int m = 0; m < M; ++m) slow |= !sinpi_in_range(u[m]);
+    if (slow) {
+        const double amp = ce[8] * 0.3183098861837907;   // ce[8] = amp * pi
+#pragma unroll
+        for (int m = 0; m < M; ++m) s[m] = amp * sincos_slow(3.141592653589793 * u[m]).x;
+        return;
+    }
+    int q[M];
+    double r[M], z[M], p[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const double t = u[m] + kWide.magic;
+        q[m] = __double2loint(t);
+        r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+        z[m] = r[m] * r[m];
+        p[m] = ce[7];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; --k)
+#pragma unroll
+        for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], ce[k]);
+#pragma unroll
+    for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], ce[8]), q[m] & 1);
 }
 
 // (A branch-free form -- no libm fall-back, r forced to 0 for finite |u| >= 2^51 so that a whole step

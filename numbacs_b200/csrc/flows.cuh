@@ -32,6 +32,7 @@ struct RhsParams {
     const double2 *coef_uv;   // Spline2D only
     double r;                 // Spline2D spherical radius
     double d[8];              // constants derived from p on the host (fill_rhs, capi.cu)
+    double e[9];              // double gyre: eps * (sinpi polynomial coefficients cp[0..7], pi)
 };
 
 #ifndef B200CS_BICKLEY_WIDE
@@ -39,6 +40,9 @@ struct RhsParams {
 #endif
 #ifndef B200CS_ABC_WIDE
 #define B200CS_ABC_WIDE 1
+#endif
+#ifndef B200CS_DG_TRIM      // round 2: eps folded into the sinpi coefficients of a(t), f / df without 2a
+#define B200CS_DG_TRIM 1
 #endif
 #ifndef B200CS_BICKLEY_NOINLINE
 #define B200CS_BICKLEY_NOINLINE 0
@@ -111,16 +115,31 @@ struct DoubleGyreT {
         double u[M], sa[M];
 #pragma unroll
         for (int m = 0; m < M; ++m) u[m] = fma(c[m], theta, phi);
+#if B200CS_DG_TRIM
+        // a(t) = eps sin(pi u) with eps folded into the polynomial's coefficients on the host
+        // (P.e = eps * {cp0..cp7, pi}, fill_rhs): one multiplication fewer per stage time
+        (void)eps;
+        sinpi12_scaled_v<M>(u, aux, P.e);
+        (void)sa;
+#else
         sinpi12_v<M>(u, sa);
 #pragma unroll
         for (int m = 0; m < M; ++m) aux[m] = eps * sa[m];
+#endif
     }
 
     template <int M>
     __device__ __forceinline__ void time_part(const double (&t)[M], double (&aux)[M]) const {
         const double eps = P.p[2];
         double arg[M], sa[M];
-#if B200CS_TIME_TURNS
+#if B200CS_TIME_TURNS && B200CS_DG_TRIM
+#pragma unroll
+        for (int m = 0; m < M; ++m) arg[m] = fma(P.d[3], t[m], P.d[4]);
+        (void)eps;
+        (void)sa;
+        sinpi12_scaled_v<M>(arg, aux, P.e);
+        return;
+#elif B200CS_TIME_TURNS
 #pragma unroll
         for (int m = 0; m < M; ++m) arg[m] = fma(P.d[3], t[m], P.d[4]);
         sinpi12_v<M>(arg, sa);
@@ -148,12 +167,17 @@ struct DoubleGyreT {
     __device__ __forceinline__ void eval(double a, double /*t*/, const double (&y)[2], double (&dy)[2]) const {
         const double c = P.d[1];     // p0 * pi*A/2 (exact scalings of pi*A)
         const double b = 1.0 - 2.0 * a;
-#if B200CS_LEAN_F
+#if B200CS_DG_TRIM
+        const double g = fma(a, y[0], b);                // a*y0 + b
+        const double f = y[0] * g;                       // a*y0**2 + b*y0
+        const double df = fma(a, y[0], g);               // 2*a*y0 + b without forming 2a
+#elif B200CS_LEAN_F
         const double f = y[0] * fma(a, y[0], b);         // a*y0**2 + b*y0, one instruction fewer
+        const double df = fma(2.0 * a, y[0], b);
 #else
         const double f = fma(a, y[0] * y[0], b * y[0]);  // a*y0**2 + b*y0
-#endif
         const double df = fma(2.0 * a, y[0], b);
+#endif
         double s[2];
 #ifdef B200CS_DG_NO_SINPI
         const double arg[2] = {kPi * (f + y[1]), kPi * (f - y[1])};

@@ -48,7 +48,8 @@
 
 #define MAXN 3
 
-enum { FLOW_DOUBLE_GYRE = 0, FLOW_BICKLEY_JET = 1, FLOW_ABC = 2, FLOW_SPLINE2D = 3, FLOW_LINEAR2D = 4 };
+enum { FLOW_DOUBLE_GYRE = 0, FLOW_BICKLEY_JET = 1, FLOW_ABC = 2, FLOW_SPLINE2D = 3, FLOW_LINEAR2D = 4,
+       FLOW_CALLBACK = 5 /* the RHS is a C function pointer (oracle/shims/numbalsoda) */ };
 enum { EXTRAP_CONSTANT = 0, EXTRAP_LINEAR = 1, EXTRAP_NEAREST = 2 };
 
 /* ------------------------------------------------------------------ spline ------------- */
@@ -234,6 +235,7 @@ typedef struct {
     int spherical;   /* 0,1,2  (flows.py:137-143) */
     double r;
     spline3_t u, v;
+    void (*callback)(double, double *, double *, double *);   /* FLOW_CALLBACK: lsoda_sig */
 } flow_t;
 
 /* Python/numba float modulo: result has the sign of the divisor (flows.py:162, 205) */
@@ -248,6 +250,9 @@ static void rhs_eval(const flow_t *f, double t, const double *y, double *dy, con
 {
     const double pi = 3.141592653589793;
     switch (f->kind) {
+    case FLOW_CALLBACK:
+        f->callback(t, (double *)y, dy, (double *)p);
+        break;
     case FLOW_DOUBLE_GYRE: { /* flows.py:1152-1158 */
         double tt = p[0] * t;
         double a = p[2] * sin(p[4] * tt + p[5]);
@@ -521,6 +526,21 @@ int oracle_dop853(const flow_t *f, int n, const double *u0, const double *t_eval
         }
         h = hnew;
     }
+}
+
+/* numbalsoda.dop853 with the RHS given as a C function pointer (the address of a numba @cfunc with
+ * signature lsoda_sig): what oracle/shims/numbalsoda calls so that the UNMODIFIED reference source
+ * runs on the same integrator.  Reentrant (the reference calls it from numba prange threads). */
+int oracle_dop853_callback(void (*rhs)(double, double *, double *, double *), int n, const double *u0,
+                           const double *t_eval, int64_t nt, double rtol, double atol, const double *p,
+                           double *usol)
+{
+    flow_t f;
+    memset(&f, 0, sizeof(f));
+    f.kind = FLOW_CALLBACK;
+    f.callback = rhs;
+    if (n < 1 || n > MAXN) return -1;
+    return oracle_dop853(&f, n, u0, t_eval, nt, rtol, atol, p, usol, NULL);
 }
 
 /* ------------------------------------------------------------------ particle loops ------ */
