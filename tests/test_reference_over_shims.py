@@ -46,14 +46,14 @@ def test_reference_test_flows_and_integration_pass_over_the_shims():
 
 def test_composition_initial_interior_over_the_shims(golden):
     code = (
-        "import numpy as np, sys\\n"
-        "from numbacs.flows import get_predefined_flow\\n"
-        "from numbacs.integration import flowmap_composition_initial\\n"
-        "from interpolation.splines import UCGrid\\n"
-        "x, y = np.linspace(0, 2, 21), np.linspace(0, 1, 11)\\n"
-        "f, p, _ = get_predefined_flow('double_gyre')\\n"
-        "fm0, fms, nT = flowmap_composition_initial(f, 0.0, 8.0, 1.0, x, y, UCGrid((x[0], x[-1], 21), (y[0], y[-1], 11)), p)\\n"
-        "np.savez(sys.argv[1], fm0=fm0, fms=fms, nT=nT)\\n")
+        "import numpy as np, sys\n"
+        "from numbacs.flows import get_predefined_flow\n"
+        "from numbacs.integration import flowmap_composition_initial\n"
+        "from interpolation.splines import UCGrid\n"
+        "x, y = np.linspace(0, 2, 21), np.linspace(0, 1, 11)\n"
+        "f, p, _ = get_predefined_flow('double_gyre')\n"
+        "fm0, fms, nT = flowmap_composition_initial(f, 0.0, 8.0, 1.0, x, y, UCGrid((x[0], x[-1], 21), (y[0], y[-1], 11)), p)\n"
+        "np.savez(sys.argv[1], fm0=fm0, fms=fms, nT=nT)\n")
     out = "/tmp/ref_shim_ci.npz"
     r = subprocess.run([sys.executable, "-c", code, out], env=_env(), cwd="/tmp", capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
