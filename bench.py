@@ -529,8 +529,7 @@ def run_b200(args):
         x_slab = x_dev[i0 - HW * has_lo:i1 + HW * has_hi]
 
         def tail():
-            vals, vecs = C_eig_2D(slab, dx, dy)
-            ft2 = ftle_from_eig(vals[:, :, 1], TINT)
+            vals, vecs, ft2 = C_eig_2D(slab, dx, dy, ftle_T=TINT)
             return ft2, ftle_ridge_pts(ft2, vecs[:, :, :, 1], x_slab, y_dev, sdd_thresh=10.0, percentile=0,
                                        spacing=(dx, dy))
 
@@ -564,7 +563,7 @@ def run_b200(args):
         ridge = {"ms": best, "n_ridge_pts": int(tt[1]),
                  "ftle_vs_ftle_grid_2D_rel_l2": float(np.sqrt(float(tt[2]) / float(tt[3]))),
                  "gather_points_ms": g_ms,
-                 "kernels": "C_eig_2D + ftle_from_eig + ftle_ridge_pts (detect, scan, compact), device-timed, "
+                 "kernels": "C_eig_2D with the FTLE fused in + ftle_ridge_pts (one-evaluation detect with a bit mask, scan, compact), device-timed, "
                             "best of 3, max over ranks; sdd_thresh=10, percentile=0",
                  "algorithmic_bytes_per_point": 64 + 16 + 2 * 24}
         del ft2, rp

@@ -244,6 +244,14 @@ B200CS_API int b200cs_c_tensor_2d(const double *flowmap_aux /*[nx,ny,n_aux,2]*/,
 B200CS_API int b200cs_c_eig_2d(const double *flowmap /*[nx,ny,2]*/, int64_t nx, int64_t ny, double dx,
                     double dy, const uint8_t *mask, double *eigvals, double *eigvecs, void *stream);
 
+/* C_eig_2D followed by ftle_from_eig(eigvals[..., 1], T) in ONE pass (diagnostics.py:200-244 and
+ * 247-269; the call pair of examples/ftle/plot_dg_ftle_ridges.py:50-56): the FTLE value is formed
+ * from the eigenvalue while it is still in registers instead of re-reading the array that was just
+ * written.  ftle [nx,ny] is bit-identical to b200cs_ftle_from_eig on the returned eigvals. */
+B200CS_API int b200cs_c_eig_ftle_2d(const double *flowmap, int64_t nx, int64_t ny, double dx, double dy,
+                         double T, const uint8_t *mask, double *eigvals, double *eigvecs, double *ftle,
+                         void *stream);
+
 /* C_eig_aux_2D(flowmap_aux, dx, dy, h, eig_main, mask)   (diagnostics.py:115-197; utils.py:49-124)
  * eig_main: eigenvalues from the main-grid tensor (centre points), eigenvectors from the aux-grid
  * tensor, on [2, nx-2) x [2, ny-2); otherwise both from the aux grid on [1, nx-1) x [1, ny-1). */

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "b200cs_ftle_series_2d": [_vp, _i64, _i64, _i64, _d, _d, _d, _vp, _vp, _vp],
     "b200cs_c_tensor_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _vp, _vp, _vp],
     "b200cs_c_eig_2d": [_vp, _i64, _i64, _d, _d, _vp, _vp, _vp, _vp],
+    "b200cs_c_eig_ftle_2d": [_vp, _i64, _i64, _d, _d, _d, _vp, _vp, _vp, _vp, _vp],
     "b200cs_c_eig_aux_2d": [_vp, _i64, _i64, _i, _d, _d, _d, _i, _vp, _vp, _vp, _vp],
     "b200cs_ftle_from_eig": [_vp, _i64, _i64, _d, _vp, _vp],
     "b200cs_ftle_ridge_pts": [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _d, _d, _d, _d, _vp, _vp, _vp,

@@ -852,6 +852,28 @@ int b200cs_c_eig_2d(const double *flowmap, int64_t nx, int64_t ny, double dx, do
     });
 }
 
+int b200cs_c_eig_ftle_2d(const double *flowmap, int64_t nx, int64_t ny, double dx, double dy, double T,
+                         const uint8_t *mask, double *eigvals, double *eigvecs, double *ftle, void *stream) {
+    return guarded([&] {
+        require_device();
+        B2_REQUIRE(flowmap && eigvals && eigvecs && ftle, "null argument");
+        B2_REQUIRE(nx >= 0 && ny >= 0, "negative grid size");
+        B2_REQUIRE(dx != 0.0 && dy != 0.0 && T != 0.0, "dx, dy and T must be non-zero");
+        if (nx == 0 || ny == 0) return;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        const size_t np = (size_t)nx * ny;
+        In<double> dfm(flowmap, np * 2, s);
+        In<uint8_t> dmask(mask, np, s);
+        Out<double> dvals(eigvals, np * 2, s), dvecs(eigvecs, np * 4, s), dft(ftle, np, s);
+        launch_c_eig(dfm.dev, nx, ny, 1, 0.0, dx, dy, /*aux_vecs=*/false, /*main_vals=*/true, dmask.dev,
+                     dvals.dev, dvecs.dev, s, dft.dev, T);
+        dvals.download();
+        dvecs.download();
+        dft.download();
+        if (dvals.staged() || dvecs.staged() || dft.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int b200cs_c_eig_aux_2d(const double *flowmap_aux, int64_t nx, int64_t ny, int n_aux, double dx, double dy,
                         double h, int eig_main, const uint8_t *mask, double *eigvals, double *eigvecs,
                         void *stream) {

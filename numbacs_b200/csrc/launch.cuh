@@ -75,7 +75,7 @@ void launch_c_tensor(const double *fm_aux, long long nx, long long ny, int n_aux
 // (aux_vecs) or the main grid.  fm is [nx, ny, n_aux, 2] (n_aux = 1: a plain flow map).
 void launch_c_eig(const double *fm, long long nx, long long ny, int n_aux, double h, double dx, double dy,
                   bool aux_vecs, bool main_vals, const uint8_t *mask, double *eigvals, double *eigvecs,
-                  cudaStream_t s);
+                  cudaStream_t s, double *ftle = nullptr, double T = 1.0);
 void launch_ftle_from_eig(const double *eigval_max, long long n, long long stride, double T, double *ftle,
                           cudaStream_t s);
 void launch_ridge_pts(const double *f, const double *ev, long long ev_pixel_stride, long long ev_comp_stride,

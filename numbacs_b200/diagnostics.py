@@ -190,9 +190,10 @@ def C_eig_aux_2D(flowmap_aux, dx, dy, h=1e-5, eig_main=True, mask=None, *, devic
     return vals.obj, vecs.obj
 
 
-def C_eig_2D(flowmap, dx, dy, mask=None, *, device_out=False):
+def C_eig_2D(flowmap, dx, dy, mask=None, *, device_out=False, ftle_T=None):
     """Eigenvalues (nx, ny, 2) and eigenvectors (nx, ny, 2, 2) of the Cauchy-Green tensor from a
-    flow map (nx, ny, 2)."""
+    flow map (nx, ny, 2).  With ftle_T = T the FTLE field ftle_from_eig(eigvals[:, :, 1], T) is
+    produced in the same pass and returned as a third array (bit-identical to the separate call)."""
     fm, ma = _lib.arg_in(flowmap), _lib.mask_in(mask)
     if fm.obj.ndim != 3 or fm.obj.shape[2] != 2:
         raise ValueError("flowmap must have shape (nx, ny, 2)")
@@ -200,6 +201,11 @@ def C_eig_2D(flowmap, dx, dy, mask=None, *, device_out=False):
     dev = bool(device_out or fm.on_device)
     vals = _lib.alloc_out((nx, ny, 2), np.float64, dev)
     vecs = _lib.alloc_out((nx, ny, 2, 2), np.float64, dev)
+    if ftle_T is not None:
+        ft = _lib.alloc_out((nx, ny), np.float64, dev)
+        _lib.check(_lib.load().b200cs_c_eig_ftle_2d(fm.ptr, nx, ny, float(dx), float(dy), float(ftle_T), ma.ptr,
+                                                    vals.ptr, vecs.ptr, ft.ptr, _lib.current_stream(dev)))
+        return vals.obj, vecs.obj, ft.obj
     _lib.check(_lib.load().b200cs_c_eig_2d(fm.ptr, nx, ny, float(dx), float(dy), ma.ptr, vals.ptr,
                                            vecs.ptr, _lib.current_stream(dev)))
     return vals.obj, vecs.obj

@@ -168,8 +168,7 @@ def _cuda_ridge_backend():
     from .extraction import ftle_ridge_pts
 
     def ridge_tail(slab, T, dx, dy, x_slab, y, sdd_thresh):
-        vals, vecs = C_eig_2D(slab, dx, dy)
-        ftle = ftle_from_eig(vals[:, :, 1], T)
+        vals, vecs, ftle = C_eig_2D(slab, dx, dy, ftle_T=T)
         return ftle, ftle_ridge_pts(ftle, vecs[:, :, :, 1], x_slab, y, sdd_thresh=sdd_thresh, percentile=0,
                                     spacing=(dx, dy))
 
