@@ -93,7 +93,46 @@ struct rhs_affine : std::false_type {};
 template <class T>
 struct rhs_affine<T, std::void_t<decltype(T::kAuxAffine)>> : std::bool_constant<T::kAuxAffine> {};
 
+// Where the stage slopes K[1..16][N] live.  RegSlopes: registers (the analytic flows: the attempt loop
+// is FP64-bound and every slope is a compile-time-indexed register).  SmemSlopes: shared memory,
+// element (s, i) of thread t at base[(s N + i) blockDim + t] (conflict-free); for the flows whose
+// right-hand side is large (64-tap spline) the ~50 registers the slopes would pin are worth more
+// as load / FMA registers of the RHS, and the ~170 shared-memory accesses per attempt are noise
+// next to its 768 coefficient loads.
+template <int N>
+struct RegSlopes {
+    static constexpr bool kDirect = true;
+    double a[17][N];
+    __device__ __forceinline__ double (&operator[](int s))[N] { return a[s]; }
+    __device__ __forceinline__ const double (&operator[](int s) const)[N] { return a[s]; }
+};
+template <int N>
+struct SmemSlopes {
+    static constexpr bool kDirect = false;
+    double *base;   // shared memory, already offset by the thread index
+    int stride;     // threads per block
+    struct Row {
+        double *p;
+        int stride;
+        __device__ __forceinline__ double &operator[](int i) const { return p[i * stride]; }
+    };
+    __device__ __forceinline__ Row operator[](int s) const { return Row{base + s * N * stride, stride}; }
+};
+
 namespace detail {
+
+// K[S] = rhs(aux, t, yy): straight into the register row, or through a temporary into shared memory
+template <class Rhs, class KS, int N>
+__device__ __forceinline__ void eval_to(const Rhs &rhs, double aux, double t, const double (&yy)[N], KS &K, int S) {
+    if constexpr (KS::kDirect) {
+        rhs.eval(aux, t, yy, K[S]);
+    } else {
+        double tmp[N];
+        rhs.eval(aux, t, yy, tmp);
+#pragma unroll
+        for (int i = 0; i < N; ++i) K[S][i] = tmp[i];
+    }
+}
 
 // a*b + c: one FMA in the product build, two roundings (the reference's arithmetic) in the strict one
 __device__ __forceinline__ double mad(double a, double b, double c) {
@@ -151,9 +190,9 @@ __device__ __forceinline__ double div_const(double a, double c, double rc) {
 }
 
 // yy = y + h * sum_j a(S,j) K_j   (j ascending, zero entries skipped at compile time)
-template <int S, int N, int... J>
+template <int S, int N, class KS, int... J>
 __device__ __forceinline__ void stage_arg(double (&yy)[N], const double (&y)[N], double h,
-                                          const double (&K)[17][N], std::integer_sequence<int, J...>) {
+                                          const KS &K, std::integer_sequence<int, J...>) {
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         double acc = 0.0;
@@ -163,12 +202,12 @@ __device__ __forceinline__ void stage_arg(double (&yy)[N], const double (&y)[N],
 }
 
 // stage S: K_S = f(x + c_S h, y + h sum a_Sj K_j); `aux` is the precomputed time-only part
-template <int S, class Rhs, int N>
+template <int S, class Rhs, int N, class KS>
 __device__ __forceinline__ void do_stage(const Rhs &rhs, double aux, double x, double h, const double (&y)[N],
-                                         double (&K)[17][N]) {
+                                         KS &K) {
     double yy[N];
     stage_arg<S, N>(yy, y, h, K, std::make_integer_sequence<int, S - 1>{});
-    rhs.eval(aux, mad(dop::kTab.c[S], h, x), yy, K[S]);
+    eval_to(rhs, aux, mad(dop::kTab.c[S], h, x), yy, K, S);
 }
 
 // time-only part of the RHS at the stage times S0 .. S0+M-1 of the step (x, h), M chains at once
@@ -190,8 +229,8 @@ __device__ __forceinline__ void stage_aux(const Rhs &rhs, double x, double h, do
     }
 }
 
-template <int R, int N, int... J>
-__device__ __forceinline__ double dense_row(const double (&K)[17][N], int i, std::integer_sequence<int, J...>) {
+template <int R, int N, class KS, int... J>
+__device__ __forceinline__ double dense_row(const KS &K, int i, std::integer_sequence<int, J...>) {
     double acc = 0.0;
     ((dop::d(R, J + 1) != 0.0 ? (void)(acc = mad(dop::kTab.d[R][J + 1], K[J + 1][i], acc)) : (void)0), ...);
     return acc;
@@ -211,15 +250,15 @@ struct NoSink {
 //   n_out  >= 2 : output times are t_k = p0 * (t0 + k*step), k = 0..n_out-1 (last = p0*(t0+T)),
 //                 rows 1..n_out-1 go to `sink`
 // Returns B200CS_ST_OK / _NMAX / _HSMALL; y holds the state reached.
-template <bool DENSE, bool LOCKSTEP, class Rhs, int N, class Sink>
+template <bool DENSE, bool LOCKSTEP, class Rhs, int N, class Sink, class KS>
 __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, double (&y)[N], double x0, double xend,
                                                 double rtol, double atol, int n_out, double out_p0,
                                                 double out_t0, double out_step, Sink &&sink,
-                                                StepCounts &cnt) {
+                                                StepCounts &cnt, KS K) {
     constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
     constexpr int kNmax = 100000;
     constexpr int kSyncEvery = B200CS_SYNC_EVERY;
-    double K[17][N];  // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages
+    // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages (registers or shared memory)
     double aux[17];   // time-only part of the RHS per stage (flows that have one)
     double x = x0;
     const double posneg = (xend - x0) < 0.0 ? -1.0 : 1.0;
@@ -242,7 +281,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
     {
         double t1[1] = {x}, a1[1] = {0.0};
         if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
-        rhs.eval(a1[0], x, y, K[1]);
+        detail::eval_to(rhs, a1[0], x, y, K, 1);
     }
     // ---- hinit (iord = 8)
     {
@@ -312,7 +351,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         {   // stage 12 is evaluated at x + h exactly
             double yy[N];
             detail::stage_arg<12, N>(yy, y, h, K, std::make_integer_sequence<int, 11>{});
-            rhs.eval(aux[12], xph, yy, K[12]);
+            detail::eval_to(rhs, aux[12], xph, yy, K, 12);
         }
         // 8th-order slope, candidate state, and the two embedded error estimates
         double y5[N];
@@ -383,7 +422,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         if (err <= 1.0) {
             // ---- accepted
             ++cnt.accepted;
-            rhs.eval(aux[12], xph, y5, K[13]);  // first-same-as-last slope, same time as stage 12
+            detail::eval_to(rhs, aux[12], xph, y5, K, 13);  // first-same-as-last slope, same time as stage 12
             if (DENSE) {
                 if (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0) {
                     ++cnt.dense;

@@ -30,6 +30,7 @@ struct KernelShape {
     static constexpr int kThreads = 128;
     static constexpr int kMinBlocks = 1;
     static constexpr bool kLockstep = false;
+    static constexpr bool kSlopesInSmem = false;
 };
 #ifndef B200CS_DG_THREADS
 #define B200CS_DG_THREADS 128
@@ -45,12 +46,19 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
     static constexpr int kThreads = B200CS_DG_THREADS;
     static constexpr int kMinBlocks = B200CS_DG_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_DG_LOCKSTEP;
+    static constexpr bool kSlopesInSmem = false;
 };
 // Bickley jet, final-time kernels: five blocks per SM (96 registers, 8 bytes of spills) measured
 // 207.9 against 204.1 M points/s uncapped (128 registers, four blocks) on config 2
 // (profiles/r1f_ab_bickley.txt)
 #ifndef B200CS_BICKLEY_MINBLOCKS
 #define B200CS_BICKLEY_MINBLOCKS 5
+#endif
+#ifndef B200CS_BICKLEY_KSMEM
+#define B200CS_BICKLEY_KSMEM false
+#endif
+#ifndef B200CS_SPLINE_KSMEM
+#define B200CS_SPLINE_KSMEM false
 #endif
 #ifndef B200CS_BICKLEY_THREADS
 #define B200CS_BICKLEY_THREADS 128
@@ -63,16 +71,31 @@ struct KernelShape<BickleyJet, false> {
     static constexpr int kThreads = B200CS_BICKLEY_THREADS;
     static constexpr int kMinBlocks = B200CS_BICKLEY_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_BICKLEY_LOCKSTEP;
+    static constexpr bool kSlopesInSmem = B200CS_BICKLEY_KSMEM;
 };
+// Round 2: with the 64-tap RHS out of line (B200CS_SPLINE_NOINLINE, flows.cuh) the attempt loop fits
+// the instruction cache, so the spline kernels run as free 128-thread blocks, five per SM (96
+// registers), like the analytic flows: 287 -> 304 M points/s on the 2701 x 1001 config-3 probe
+// (profiles/r2_ab_spline.txt; lockstep 512 x 1 was the round-1 shape, kept as an A/B option).
+// What bounds the kernel now is the L1 data pipe: 64 taps x 16 B per lane and RHS = 256 wavefronts
+// per warp-RHS, measured at 60 % of the pipe's peak (profiles/r2a_flowmap_spline_c3.txt); parking
+// the stage slopes in shared memory (B200CS_SPLINE_KSMEM) to free registers changed nothing.
 #ifndef B200CS_SPLINE_THREADS
-#define B200CS_SPLINE_THREADS 512
+#define B200CS_SPLINE_THREADS 128
+#endif
+#ifndef B200CS_SPLINE_MINBLOCKS
+#define B200CS_SPLINE_MINBLOCKS 5
+#endif
+#ifndef B200CS_SPLINE_LOCKSTEP
+#define B200CS_SPLINE_LOCKSTEP false
 #endif
 template <int SPH>
 struct KernelShape<Spline2D<SPH, false>, false> {
     static constexpr int kThreads = B200CS_SPLINE_THREADS;   // 512 x 128 registers = the whole register file
                                                              // (measured: 448 -> 246, 512 -> 281, 640 (96 regs, spills) -> 276 M points/s)
-    static constexpr int kMinBlocks = 1;
-    static constexpr bool kLockstep = true;
+    static constexpr int kMinBlocks = B200CS_SPLINE_MINBLOCKS;
+    static constexpr bool kLockstep = B200CS_SPLINE_LOCKSTEP;
+    static constexpr bool kSlopesInSmem = B200CS_SPLINE_KSMEM;
 };
 
 template <int N>
@@ -163,6 +186,12 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
 
     const Rhs rhs(A.rhs);
     const bool integrate = active && (xend != x0);   // T == 0: the flow map is the identity
+    constexpr bool kKSmem = KernelShape<Rhs, DENSE>::kSlopesInSmem;
+    __shared__ double slopes_smem[kKSmem ? (DENSE ? 17 : 14) * N * kBlock : 1];
+    auto slopes = [&] {
+        if constexpr (kKSmem) return SmemSlopes<N>{slopes_smem + threadIdx.x, kBlock};
+        else return RegSlopes<N>{};
+    };
     if (DENSE) {
         RowSink<N> sink{row, A.out_aligned16 != 0};
         if (active) {
@@ -173,10 +202,10 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
             for (long long k = 0; k < row_len; ++k) row[k] = 0.0;  // masked: zeros (integration.py:163, 515)
         }
         status = dop853_integrate<true, kLockstep>(rhs, integrate, y, x0, xend, A.rtol, A.atol, A.n_out,
-                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt);
+                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt, slopes());
     } else {
         status = dop853_integrate<false, kLockstep>(rhs, integrate, y, x0, xend, A.rtol, A.atol, 0, 0.0, 0.0,
-                                                    0.0, NoSink<N>{}, cnt);
+                                                    0.0, NoSink<N>{}, cnt, slopes());
     }
     if (active && !integrate) status = B200CS_ST_OK;
 
@@ -272,7 +301,7 @@ __global__ void __launch_bounds__(128) lavd_flowmap_kernel(const __grid_constant
             for (int k = 1; k < A.n_out; ++k) sink(k, y);
         } else {
             status = dop853_integrate<true, false>(rhs, true, y, A.x0, A.xend, A.rtol, A.atol, A.n_out,
-                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt);
+                                                   A.out_p0, A.out_t0, A.out_step, sink, cnt, RegSlopes<Rhs::N>{});
         }
         lavd = sink.finish(fabs(A.tspan_phys[1] - A.tspan_phys[0]));
     }

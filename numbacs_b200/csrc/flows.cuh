@@ -44,6 +44,9 @@ struct RhsParams {
 #ifndef B200CS_DG_TRIM      // round 2: eps folded into the sinpi coefficients of a(t), f / df without 2a
 #define B200CS_DG_TRIM 1
 #endif
+#ifndef B200CS_SPLINE_NOINLINE
+#define B200CS_SPLINE_NOINLINE 1
+#endif
 #ifndef B200CS_BICKLEY_NOINLINE
 #define B200CS_BICKLEY_NOINLINE 0
 #endif
@@ -359,7 +362,28 @@ struct Spline2D {
     __device__ __forceinline__ explicit Spline2D(const RhsParams &P_) : P(P_) {}
     template <int M>
     __device__ __forceinline__ void time_part(const double (&)[M], double (&)[M]) const {}
+#if B200CS_SPLINE_NOINLINE
+    // The 64-tap RHS is ~650 instructions; inlined into 12 stages + FSAL + hinit the attempt loop is
+    // several times the 32 KB instruction cache, which is why this kernel ran in lockstep blocks.
+    // Out of line there is one copy: the loop fits the cache and blocks can run free.
+    static __device__ __noinline__ double2 eval_ool(const RhsParams *Pp, double t, double y0, double y1) {
+        const Spline2D self(*Pp);
+        const double y[2] = {y0, y1};
+        double dy[2];
+        self.eval_body(t, y, dy);
+        return make_double2(dy[0], dy[1]);
+    }
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
+        const double2 r = eval_ool(&P, t, y[0], y[1]);
+        dy[0] = r.x;
+        dy[1] = r.y;
+    }
+#else
+    __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
+        eval_body(t, y, dy);
+    }
+#endif
+    __device__ __forceinline__ void eval_body(double t, const double (&y)[2], double (&dy)[2]) const {
         const double p0 = P.p[0];
         double xx = y[0];
         const double yy = y[1];

@@ -14,6 +14,9 @@
 #ifndef B200CS_STRICT
 #define B200CS_STRICT 0
 #endif
+#ifndef B200CS_LOCATE_MAGIC
+#define B200CS_LOCATE_MAGIC 0
+#endif
 #ifndef B200CS_STRICT_RHS   // the right-hand-side half of the strict build on its own (A/B decomposition)
 #define B200CS_STRICT_RHS B200CS_STRICT
 #endif
@@ -41,6 +44,21 @@ __device__ __forceinline__ void axis_locate(const SplineGridDev &g, int d, doubl
     fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
     i = (int)fi;
     lam = __dsub_rn(dd, __dmul_rn(fi, delta)) / delta;
+#elif B200CS_LOCATE_MAGIC
+    // floor() and the double -> int conversion without FRND.F64 / F2I.F64 (each costs ~3.7 DFMA issue
+    // slots on sm_100, profiles/r2_ubench_fp64_conversions.txt): k = rint(u) by the 1.5 * 2^52 magic
+    // constant (its low word is the integer), minus one where the rounding went up; clamped as integers.
+    const double u = dd * g.inv_delta[d];
+    const double tm = u + 6755399441055744.0;
+    const double kr = tm - 6755399441055744.0;
+    int k = __double2loint(tm) - (kr > u ? 1 : 0);
+    // |u| >= 2^31 (a particle absurdly far outside the grid) or NaN: the clamp decides
+    if (!(fabs(u) < 2.0e9)) k = (u > 0.0) ? g.n[d] - 2 : 0;
+    k = max(0, min(k, g.n[d] - 2));
+    i = k;
+    const double fi = __hiloint2double(0x43300000, k ^ 0x80000000) - 4503601774854144.0;   // (double)k, k >= 0
+    const double r = __dsub_rn(dd, __dmul_rn(fi, g.delta[d]));
+    lam = r * g.inv_delta[d];
 #else
     double fi = floor(dd * g.inv_delta[d]);
     fi = fmin(fmax(fi, 0.0), (double)(g.n[d] - 2));
