@@ -110,6 +110,19 @@ B200CS_API int b200cs_prefilter_3d(const double *data, int64_t n0, int64_t n1, i
 /* evaluate a scalar handle at npts points (t, x, y): get_callable_scalar(...)(pts) */
 B200CS_API int b200cs_scalar_eval(int handle, const double *pts /*[npts,3]*/, int64_t npts,
                        double *out /*[npts]*/, void *stream);
+/* get_callable_2D(grid_vel, C_eval_u, C_eval_v, spherical, extrap_mode, r)(point)   (flows.py:261-384):
+ * (u, v) of an interpolated velocity field (a handle from b200cs_flow_create_spline / _linear) at
+ * pts [npts,3] = (t, x, y) -> uv [npts,2].  Callable semantics, not right-hand-side semantics: no
+ * params[0], no longitude wrap; spherical == 1 applies the 180 / (pi r cos) scaling, any other
+ * value returns the raw interpolant, as the reference does. */
+B200CS_API int b200cs_velocity_eval(int flow, const double *pts, int64_t npts, double *uv, void *stream);
+
+/* curl_func_tspan(fnc, t, x, y, h)   (utils.py:570-608) with fnc = the callable above:
+ * curl [nt,nx,ny] of the velocity by central differences of spacing h at every (t_k, x_i, y_j)
+ * (the vorticity field of examples/elliptic_lcs/plot_qge_elliptic_lcs.py:60-62). */
+B200CS_API int b200cs_curl_func_tspan(int flow, const double *t, int64_t nt, const double *x, int64_t nx,
+                           const double *y, int64_t ny, double h, double *curl, void *stream);
+
 /* evaluate the RHS of a flow at npts states: dy = rhs(t[q], y[q,:], params)  (lsoda_sig cfunc) */
 B200CS_API int b200cs_flow_rhs(int flow, const double *t /*[npts]*/, const double *y /*[npts,ndim]*/,
                     int64_t npts, const double *params, int nparams, double *dy /*[npts,ndim]*/,

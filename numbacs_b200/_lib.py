@@ -34,6 +34,8 @@ PROTOTYPES = {
     "b200cs_flow_info": [_i, _ip, _ip, _ip],
     "b200cs_prefilter_3d": [_vp, _i64, _i64, _i64, _vp, _vp],
     "b200cs_scalar_eval": [_i, _vp, _i64, _vp, _vp],
+    "b200cs_velocity_eval": [_i, _vp, _i64, _vp, _vp],
+    "b200cs_curl_func_tspan": [_i, _vp, _i64, _vp, _i64, _vp, _i64, _d, _vp, _vp],
     "b200cs_flow_rhs": [_i, _vp, _vp, _i64, _vp, _i, _vp, _vp],
     "b200cs_flowmap_grid_2d": [_i, _d, _d, _vp, _i64, _vp, _i64, _vp, _i, _i, _d, _d, _vp, _i,
                                _vp, _vp, _vp, _vp, _vp, _vp],

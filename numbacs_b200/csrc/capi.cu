@@ -405,6 +405,44 @@ int b200cs_scalar_eval(int handle, const double *pts, int64_t npts, double *out,
     });
 }
 
+int b200cs_velocity_eval(int flow, const double *pts, int64_t npts, double *uv, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(flow);
+        B2_REQUIRE(f->kind == B200CS_FLOW_SPLINE2D || f->kind == B200CS_FLOW_LINEAR2D,
+                   "handle %d is not an interpolated velocity field", flow);
+        check_device(*f);
+        B2_REQUIRE(npts >= 0 && (npts == 0 || (pts && uv)), "null argument");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> dp(pts, (size_t)npts * 3, s);
+        Out<double> dout(uv, (size_t)npts * 2, s);
+        launch_velocity_eval(*f, dp.dev, npts, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int b200cs_curl_func_tspan(int flow, const double *t, int64_t nt, const double *x, int64_t nx, const double *y,
+                           int64_t ny, double h, double *curl, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(flow);
+        B2_REQUIRE(f->kind == B200CS_FLOW_SPLINE2D || f->kind == B200CS_FLOW_LINEAR2D,
+                   "handle %d is not an interpolated velocity field", flow);
+        check_device(*f);
+        B2_REQUIRE(nt >= 0 && nx >= 0 && ny >= 0, "negative size");
+        B2_REQUIRE(h != 0.0, "h must be non-zero");
+        if (nt == 0 || nx == 0 || ny == 0) return;
+        B2_REQUIRE(t && x && y && curl, "null argument");
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        In<double> dt(t, nt, s), dx(x, nx, s), dy(y, ny, s);
+        Out<double> dout(curl, (size_t)nt * nx * ny, s);
+        launch_curl_tspan(*f, dt.dev, nt, dx.dev, nx, dy.dev, ny, h, dout.dev, s);
+        dout.download();
+        if (dout.staged()) B2_CHECK_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
 int b200cs_flow_rhs(int flow, const double *t, const double *y, int64_t npts, const double *params,
                     int nparams, double *dy, void *stream) {
     return guarded([&] {

@@ -38,6 +38,52 @@ __global__ void scalar_eval_kernel(const __grid_constant__ ScalarDev S, const do
     out[q] = scalar_at(S, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2]);
 }
 
+// get_callable_2D (flows.py:261-384): (u, v) of the spline velocity at (t, x, y) -- no params[0],
+// no longitude wrap; spherical == 1 scales by 180 / (pi r cos(y pi / 180)) and 180 / (pi r) in the
+// reference's operation order (296-325), every other value of `spherical` returns the raw spline
+// values (the reference only tests `spherical == 1`).
+__device__ __forceinline__ void velocity_at(const SplineGridDev &g, const double2 *__restrict__ C, bool linear,
+                                            int spherical, double r, double t, double x, double y, double &u,
+                                            double &v) {
+    if (linear) eval_linear_uv(g, C, t, x, y, u, v);
+    else eval_spline_uv(g, C, t, x, y, u, v);
+    if (spherical == 1) {
+        const double pi = 3.141592653589793;
+        u = __ddiv_rn(__dmul_rn(u, 180.0), __dmul_rn(__dmul_rn(pi, r), cos(__ddiv_rn(__dmul_rn(y, pi), 180.0))));
+        v = __ddiv_rn(__dmul_rn(v, 180.0), __dmul_rn(pi, r));
+    }
+}
+
+__global__ void velocity_eval_kernel(const SplineGridDev g, const double2 *__restrict__ C, int linear, int spherical,
+                                     double r, const double *__restrict__ pts, long long npts,
+                                     double *__restrict__ out) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= npts) return;
+    double u, v;
+    velocity_at(g, C, linear != 0, spherical, r, pts[3 * q], pts[3 * q + 1], pts[3 * q + 2], u, v);
+    out[2 * q] = u;
+    out[2 * q + 1] = v;
+}
+
+// curl_func_tspan (utils.py:570-608): central differences of the velocity callable with spacing h,
+// curl[k, i, j] = (v(t_k, x_i + h, y_j) - v(t_k, x_i - h, y_j)) / (2h) - (u(.., y_j + h) - u(.., y_j - h)) / (2h)
+__global__ void curl_tspan_kernel(const SplineGridDev g, const double2 *__restrict__ C, int linear, int spherical,
+                                  double r, const double *__restrict__ t, long long nt, const double *__restrict__ x,
+                                  long long nx, const double *__restrict__ y, long long ny, double h,
+                                  double *__restrict__ curl) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nt * nx * ny) return;
+    const long long k = q / (nx * ny), rem = q - k * nx * ny, i = rem / ny, j = rem - i * ny;
+    const double tk = t[k], xi = x[i], yj = y[j];
+    double u0, v0, u1, v1, ua, va, ub, vb;
+    velocity_at(g, C, linear != 0, spherical, r, tk, __dadd_rn(xi, h), yj, u1, v1);
+    velocity_at(g, C, linear != 0, spherical, r, tk, __dsub_rn(xi, h), yj, u0, v0);
+    velocity_at(g, C, linear != 0, spherical, r, tk, xi, __dadd_rn(yj, h), ub, vb);
+    velocity_at(g, C, linear != 0, spherical, r, tk, xi, __dsub_rn(yj, h), ua, va);
+    const double two_h = __dmul_rn(2.0, h);
+    curl[q] = __dsub_rn(__ddiv_rn(__dsub_rn(v1, v0), two_h), __ddiv_rn(__dsub_rn(ub, ua), two_h));
+}
+
 constexpr int kRedThreads = 256;
 
 // partial[k * gridDim.x + b] = sum over the block's strided share of the points
@@ -224,6 +270,24 @@ ScalarDev make_scalar_dev(const FlowSpec &f) {
     S.C = static_cast<const double *>(f.coef);
     S.linear = f.linear;
     return S;
+}
+
+void launch_velocity_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s) {
+    if (npts <= 0) return;
+    velocity_eval_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, s>>>(
+        make_grid_dev(f), static_cast<const double2 *>(f.coef), f.linear ? 1 : 0, f.spherical, f.r, pts, npts, out);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
+void launch_curl_tspan(const FlowSpec &f, const double *t, long long nt, const double *x, long long nx,
+                       const double *y, long long ny, double h, double *curl, cudaStream_t s) {
+    const long long n = nt * nx * ny;
+    if (n <= 0) return;
+    B2_REQUIRE((n + 127) / 128 < 2147483647LL, "too many points for one curl launch");
+    curl_tspan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(make_grid_dev(f), static_cast<const double2 *>(f.coef),
+                                                                  f.linear ? 1 : 0, f.spherical, f.r, t, nt, x, nx, y,
+                                                                  ny, h, curl);
+    B2_CHECK_CUDA(cudaGetLastError());
 }
 
 void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s) {

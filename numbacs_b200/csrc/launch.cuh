@@ -55,6 +55,9 @@ void launch_ftle(const double *fm, long long nx, long long ny, double T, double 
 SplineGridDev make_grid_dev(const FlowSpec &f);
 
 void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s);
+void launch_velocity_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s);
+void launch_curl_tspan(const FlowSpec &f, const double *t, long long nt, const double *x, long long nx,
+                       const double *y, long long ny, double h, double *curl, cudaStream_t s);
 void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
                       const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s);
 ScalarDev make_scalar_dev(const FlowSpec &f);

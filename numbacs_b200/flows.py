@@ -17,7 +17,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["get_predefined_flow", "get_interp_arrays_2D", "get_interp_arrays_scalar", "get_flow_linear_2D",
-           "get_flow_2D", "get_callable_scalar", "get_callable_scalar_linear", "ScalarField",
+           "get_flow_2D", "get_callable_2D", "get_callable_scalar", "get_callable_scalar_linear", "ScalarField",
            "release_flow"]
 
 
@@ -140,6 +140,41 @@ def get_flow_linear_2D(grid_vel, U, V, spherical=0, extrap_mode="constant", r=63
         C.c_void_p(g.ctypes.data), ua.ptr, va.ptr, int(spherical), _lib.EXTRAP[extrap_mode],
         float(r), C.byref(h)))
     return h.value
+
+
+class VelocityField:
+    """Device-resident velocity interpolant (the object get_callable_2D returns).  Callable like the
+    reference's jit function: vel(point[3]) -> array([u, v]) (or the tuple (u, v) with
+    return_type="tuple"); vel(points[N, 3]) -> array[N, 2].  numbacs_b200.utils.curl_func_tspan
+    recognises it and differentiates it on the GPU."""
+
+    def __init__(self, handle, return_type):
+        self.handle = handle
+        self.return_type = return_type
+
+    def __call__(self, pts):
+        single = (not _lib._is_torch(pts)) and np.ndim(pts) == 1
+        p = _lib.arg_in(np.atleast_2d(pts) if single else pts)
+        n = int(p.obj.shape[0])
+        out = _lib.alloc_out((n, 2), np.float64, p.on_device)
+        _lib.check(_lib.load().b200cs_velocity_eval(self.handle, p.ptr, n, out.ptr,
+                                                    _lib.current_stream(p.on_device)))
+        if not single:
+            return out.obj
+        if self.return_type == "tuple":
+            return float(out.obj[0, 0]), float(out.obj[0, 1])
+        return np.array([out.obj[0, 0], out.obj[0, 1]], np.float64)
+
+
+def get_callable_2D(grid_vel, C_eval_u, C_eval_v, spherical=0, extrap_mode="constant", r=6371.0,
+                    return_type="array"):
+    """Callable spline of the velocity field (flows.py:261-384), evaluated on the device.  As in the
+    reference only spherical == 1 applies the spherical scaling; there is no longitude wrap and no
+    params[0] in a callable."""
+    if return_type not in ("array", "tuple"):
+        raise ValueError("return_type must be 'array' or 'tuple'")
+    h = get_flow_2D(grid_vel, C_eval_u, C_eval_v, 1 if spherical == 1 else 0, extrap_mode, r)
+    return VelocityField(h, return_type)
 
 
 def release_flow(funcptr):

@@ -10,7 +10,25 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["binary_mask_dilation", "fill_nans_and_get_mask"]
+__all__ = ["binary_mask_dilation", "fill_nans_and_get_mask", "curl_func_tspan"]
+
+
+def curl_func_tspan(fnc, t, x, y, h=1e-3, *, device_out=False):
+    """Curl (vorticity) of the velocity callable `fnc` over times t and the grid (x, y) by central
+    differences of spacing h -> (nt, nx, ny)   (utils.py:570-608; the vorticity field of
+    examples/elliptic_lcs/plot_qge_elliptic_lcs.py:60).  `fnc` must come from
+    numbacs_b200.flows.get_callable_2D: an arbitrary jit-callable cannot run on the GPU."""
+    from .flows import VelocityField
+    if not isinstance(fnc, VelocityField):
+        raise NotImplementedError("fnc must come from numbacs_b200.flows.get_callable_2D: an arbitrary "
+                                  "jit-callable cannot run on the GPU and there is no CPU fallback")
+    ta, xa, ya = _lib.arg_in(t), _lib.arg_in(x), _lib.arg_in(y)
+    nt, nx, ny = int(ta.obj.shape[0]), int(xa.obj.shape[0]), int(ya.obj.shape[0])
+    dev = bool(device_out or ta.on_device or xa.on_device or ya.on_device)
+    out = _lib.alloc_out((nt, nx, ny), np.float64, dev)
+    _lib.check(_lib.load().b200cs_curl_func_tspan(fnc.handle, ta.ptr, nt, xa.ptr, nx, ya.ptr, ny, float(h),
+                                                  out.ptr, _lib.current_stream(dev)))
+    return out.obj
 
 
 def binary_mask_dilation(mask, corners=False, *, device_out=False):
