@@ -99,6 +99,13 @@ B200CS_API int b200cs_scalar_create(const double *grid9, const double *data, int
                          int *out_handle);
 
 B200CS_API int b200cs_flow_destroy(int handle);   /* flows and scalar fields share one handle space */
+/* Number of right-hand-side evaluations of an interpolated flow (b200cs_flow_create_spline /
+ * _linear) that fell OUTSIDE its data grid since the counter was last reset, summed over every
+ * launch that used the handle; 0 for analytic flows.  Synchronises `stream`.  The reference has no
+ * such diagnostic: it is the guard on the extrapolation modes of interpolation.splines, whose
+ * out-of-grid behaviour no reference test pins -- parity runs assert 0. */
+B200CS_API int b200cs_flow_out_of_grid(int flow, int64_t *count, int reset, void *stream);
+
 /* kind (B200CS_FLOW_* or -1 for a scalar field), state dimension, minimum length of params */
 B200CS_API int b200cs_flow_info(int handle, int *kind, int *ndim, int *min_params);
 

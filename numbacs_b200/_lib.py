@@ -32,6 +32,7 @@ PROTOTYPES = {
     "b200cs_scalar_create": [_vp, _vp, _i, _i, _ip],
     "b200cs_flow_destroy": [_i],
     "b200cs_flow_info": [_i, _ip, _ip, _ip],
+    "b200cs_flow_out_of_grid": [_i, _vp, _i, _vp],
     "b200cs_prefilter_3d": [_vp, _i64, _i64, _i64, _vp, _vp],
     "b200cs_scalar_eval": [_i, _vp, _i64, _vp, _vp],
     "b200cs_velocity_eval": [_i, _vp, _i64, _vp, _vp],

@@ -40,6 +40,33 @@ bool is_device_ptr(const void *p) {
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
+bool is_pinned_host_ptr(const void *p) {
+    cudaPointerAttributes attr{};
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();  // clear
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// Upload of a host array into stream-ordered scratch.  From pageable memory cudaMemcpyAsync returns
+// once the source has been staged, so the caller may drop its array as soon as the API call
+// returns.  From PINNED memory the copy is truly asynchronous: the call would return while the DMA
+// has not read the buffer yet (a pinned torch tensor that the Python wrapper releases right after
+// the call).  For those the host waits for THIS copy only (an event behind it), not for the stream.
+void upload_to_scratch(void *dst, const void *src, size_t bytes, cudaStream_t s) {
+    B2_CHECK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+    if (is_pinned_host_ptr(src)) {
+        cudaEvent_t ev;
+        B2_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        cudaError_t e = cudaEventRecord(ev, s);
+        if (e == cudaSuccess) e = cudaEventSynchronize(ev);
+        cudaEventDestroy(ev);
+        B2_CHECK_CUDA(e);
+    }
+}
+
 // ---------------------------------------------------------------- registry
 static std::mutex g_reg_mu;
 static std::unordered_map<int, std::shared_ptr<FlowSpec>> g_reg;
@@ -139,6 +166,7 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
     }
     if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
     R.coef_uv = nullptr;
+    R.oog = f.oog;
     R.r = f.r;
     std::memset(&R.grid, 0, sizeof(R.grid));
     if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
@@ -313,6 +341,8 @@ static void create_gridded_flow(const double *grid9, const double *Cu, const dou
     const size_t count = (size_t)(f->grid.n[0] + pad) * (f->grid.n[1] + pad) * (f->grid.n[2] + pad);
     f->coef_bytes = count * sizeof(double2);
     B2_CHECK_CUDA(cudaMalloc(&f->coef, f->coef_bytes));
+    B2_CHECK_CUDA(cudaMalloc(&f->oog, sizeof(unsigned long long)));
+    B2_CHECK_CUDA(cudaMemset(f->oog, 0, sizeof(unsigned long long)));
     cudaStream_t s = nullptr;
     {
         In<double> du(Cu, count, s), dv(Cv, count, s);
@@ -361,6 +391,23 @@ int b200cs_flow_destroy(int handle) {
             set_error("unknown flow handle %d", handle);
             throw Fail{B200CS_E_HANDLE};
         }
+    });
+}
+
+int b200cs_flow_out_of_grid(int flow, int64_t *count, int reset, void *stream) {
+    return guarded([&] {
+        require_device();
+        auto f = registry_get(flow);
+        B2_REQUIRE(count, "count is null");
+        *count = 0;
+        if (!f->oog) return;    // analytic flows have no data grid
+        check_device(*f);
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        unsigned long long v = 0;
+        B2_CHECK_CUDA(cudaMemcpyAsync(&v, f->oog, sizeof(v), cudaMemcpyDeviceToHost, s));
+        if (reset) B2_CHECK_CUDA(cudaMemsetAsync(f->oog, 0, sizeof(v), s));
+        B2_CHECK_CUDA(cudaStreamSynchronize(s));
+        *count = (int64_t)v;
     });
 }
 

@@ -56,6 +56,8 @@ int guarded(F &&f) {
 
 // ---------------------------------------------------------------- pointer staging
 bool is_device_ptr(const void *p);
+bool is_pinned_host_ptr(const void *p);
+void upload_to_scratch(void *dst, const void *src, size_t bytes, cudaStream_t s);   // capi.cu
 
 // Stream-ordered scratch buffer (cudaMallocAsync), freed on the same stream.
 struct Scratch {
@@ -94,7 +96,7 @@ struct In {
             dev = p;
         } else {
             tmp = Scratch(count * sizeof(T), s);
-            B2_CHECK_CUDA(cudaMemcpyAsync(tmp.ptr, p, count * sizeof(T), cudaMemcpyHostToDevice, s));
+            upload_to_scratch(tmp.ptr, p, count * sizeof(T), s);
             dev = static_cast<const T *>(tmp.ptr);
         }
     }
@@ -120,8 +122,7 @@ struct Out {
             host = p;
             tmp = Scratch(n * sizeof(T), s);
             dev = static_cast<T *>(tmp.ptr);
-            if (upload_first)
-                B2_CHECK_CUDA(cudaMemcpyAsync(dev, p, n * sizeof(T), cudaMemcpyHostToDevice, s));
+            if (upload_first) upload_to_scratch(dev, p, n * sizeof(T), s);
         }
     }
     Out(Out &&) = default;
@@ -152,8 +153,12 @@ struct FlowSpec {
     double r = 6371.0;
     void *coef = nullptr;  // device: double2 (u,v) interleaved for flows, double for scalars
     size_t coef_bytes = 0;
+    // interpolated flows: device counter of right-hand-side evaluations that fell outside the data
+    // grid (where the extrapolation modes, unpinned by any reference test, decide the value)
+    unsigned long long *oog = nullptr;
     ~FlowSpec() {
         if (coef) cudaFree(coef);
+        if (oog) cudaFree(oog);
     }
 };
 

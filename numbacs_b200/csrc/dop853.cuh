@@ -492,6 +492,14 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         } while (0);
     }
     if (DENSE && status == B200CS_ST_OK && n_out >= 2) sink(n_out - 1, y);
+    if (DENSE && n_out >= 2 && (status == B200CS_ST_NMAX || status == B200CS_ST_HSMALL)) {
+        // the integration gave up: the rows it never reached are NaN, not whatever the output
+        // buffer held (the reference's numbalsoda leaves them unspecified and ignores `success`)
+        double bad[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) bad[i] = __longlong_as_double(0x7ff8000000000000LL);
+        for (int k = iout; k < n_out; ++k) sink(k, bad);
+    }
     return status;
 }
 

@@ -33,6 +33,7 @@ struct RhsParams {
     double r;                 // Spline2D spherical radius
     double d[8];              // constants derived from p on the host (fill_rhs, capi.cu)
     double e[9];              // double gyre: eps * (sinpi polynomial coefficients cp[0..7], pi)
+    unsigned long long *oog;  // Spline2D: out-of-grid evaluation counter of the flow (may be null)
 };
 
 #ifndef B200CS_BICKLEY_WIDE
@@ -390,8 +391,15 @@ struct Spline2D {
         if (SPHERICAL == 1) xx = pymod_pos(y[0] - 180.0, 360.0) - 180.0;
         if (SPHERICAL == 2) xx = pymod_pos(y[0], 360.0);
         double u, v;
-        if (LINEAR) eval_linear_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
-        else eval_spline_uv(P.grid, P.coef_uv, p0 * t, xx, yy, u, v);
+        const double tt = p0 * t;
+        // count evaluations outside the data grid (the only guard on the extrapolation
+        // modes, which no reference test pins); a particle that stays inside never takes the branch
+        if (tt < P.grid.a[0] || tt > P.grid.b[0] || xx < P.grid.a[1] || xx > P.grid.b[1] || yy < P.grid.a[2] ||
+            yy > P.grid.b[2]) {
+            if (P.oog) atomicAdd(P.oog, 1ULL);
+        }
+        if (LINEAR) eval_linear_uv(P.grid, P.coef_uv, tt, xx, yy, u, v);
+        else eval_spline_uv(P.grid, P.coef_uv, tt, xx, yy, u, v);
         if (SPHERICAL) {
             // ((p0*u)*180) / (pi*r*cos(yy*pi/180))   (flows.py:165-196)
 #if B200CS_STRICT_RHS

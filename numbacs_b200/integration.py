@@ -50,6 +50,15 @@ def _info_bufs(info, shape, device):
     return status, steps, stats
 
 
+def out_of_grid_count(funcptr, reset=True, device=False):
+    """Evaluations of an interpolated flow outside its data grid since the last reset (0 for analytic
+    flows): the guard on the unpinned extrapolation modes (b200cs_flow_out_of_grid)."""
+    n = np.zeros(1, np.int64)
+    _lib.check(_lib.load().b200cs_flow_out_of_grid(int(funcptr), C.c_void_p(n.ctypes.data), int(bool(reset)),
+                                                   _lib.current_stream(device)))
+    return int(n[0])
+
+
 def _fill_info(info, status, steps, stats):
     if info is not None:
         info["status"], info["steps"], info["stats"] = status.obj, steps.obj, stats.obj
@@ -69,6 +78,8 @@ def _grid(funcptr, t0, T, x, y, params, n, method, rtol, atol, mask, device_out,
         _method(method), float(rtol), float(atol), ma.ptr, int(n), out.ptr,
         C.c_void_p(tspan.ctypes.data), status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
     _fill_info(info, status, steps, stats)
+    if info is not None:
+        info["out_of_grid"] = out_of_grid_count(funcptr, True, dev)
     return out.obj, tspan
 
 
@@ -86,6 +97,8 @@ def _pts(funcptr, t0, T, pts, params, n, method, rtol, atol, mask, device_out, i
         _method(method), float(rtol), float(atol), ma.ptr, int(n), out.ptr,
         C.c_void_p(tspan.ctypes.data), status.ptr, steps.ptr, stats.ptr, _lib.current_stream(dev)))
     _fill_info(info, status, steps, stats)
+    if info is not None:
+        info["out_of_grid"] = out_of_grid_count(funcptr, True, dev)
     return out.obj, tspan
 
 

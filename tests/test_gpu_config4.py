@@ -73,3 +73,41 @@ def test_config4_chain_matches_the_reference(nb, G):
     assert vd.is_cuda and np.array_equal(vd.cpu().numpy(), vort)
     with pytest.raises(NotImplementedError):
         nb.utils.curl_func_tspan(lambda p: p, tspan, xg, yg)
+
+
+def test_out_of_grid_counter(nb, G):
+    """info['out_of_grid'] counts right-hand-side evaluations outside the data grid (the guard on the
+    extrapolation modes, which no reference test pins): 0 for particles that stay inside, > 0 once a
+    particle starts outside, 0 again for the next call (the counter is reset when it is read)."""
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(G["t"], G["x"], G["y"], G["U"], G["V"])
+    f = nb.flows.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")
+    params = np.array([1.0])
+    info = {}
+    nb.integration.flowmap_grid_2D(f, 0.3, 0.4, G["xg"], G["yg"], params, info=info)
+    assert info["out_of_grid"] == 0
+    info = {}
+    nb.integration.flowmap(f, 0.3, 0.4, np.array([[0.5, 1.0], [1.5, 1.0], [0.5, -0.2]]), params, info=info)
+    assert info["out_of_grid"] > 0
+    assert nb.integration.out_of_grid_count(f) == 0
+    info = {}
+    nb.integration.flowmap(f, 0.9, 0.4, np.array([[0.5, 1.0]]), params, info=info)   # leaves the grid in TIME
+    assert info["out_of_grid"] > 0
+    fa, pa, _ = nb.flows.get_predefined_flow("double_gyre")
+    info = {}
+    nb.integration.flowmap_grid_2D(fa, 0.0, 1.0, np.linspace(0, 2, 5), np.linspace(0, 1, 4), pa, info=info)
+    assert info["out_of_grid"] == 0                                                # analytic flows have no grid
+
+
+def test_dense_rows_of_a_failed_integration_are_nan(nb):
+    """A particle whose integration gives up (NaN state -> step size underflow) leaves NaN in the
+    output rows it never reached instead of uninitialised memory; the other particles are untouched."""
+    f, p, _ = nb.flows.get_predefined_flow("double_gyre")
+    pts = np.array([[0.5, 0.5], [np.nan, 0.3], [1.5, 0.25]])
+    info = {}
+    fmn, ts = nb.integration.flowmap_n(f, 0.0, 4.0, pts, p, n=6, info=info)
+    st = np.asarray(info["status"])
+    assert st[0] == 1 and st[2] == 1 and st[1] != 1
+    assert np.isfinite(fmn[0]).all() and np.isfinite(fmn[2]).all()
+    assert np.isnan(fmn[1, 1:]).all()
+    ok, _ = nb.integration.flowmap_n(f, 0.0, 4.0, pts[[0, 2]], p, n=6)
+    assert np.array_equal(ok, fmn[[0, 2]])
