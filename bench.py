@@ -260,11 +260,36 @@ class ClockSampler:
 
 # ------------------------------------------------------------------ the B200 arm
 
-def shared_pinned(name, count, create):
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (sysfs), so that the host pages
+    it first-touches -- its slice of the shared result buffers -- are allocated next to the PCIe root
+    the GPU writes through.  Returns the node or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(gpu_index)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out            # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def shared_pinned(name, count, create, own=None):
     """A float64 host buffer of `count` elements that every rank of the node maps (POSIX shared
-    memory) and registers with CUDA, so each GPU downloads its rows of the assembled result
-    straight into its slice -- the final gather to host memory uses all PCIe links at once and
-    rank 0 ends up holding the whole field.  Returns (tensor, path) or (None, None)."""
+    memory), so each GPU downloads its rows of the assembled result straight into its slice -- the
+    final gather to host memory uses all PCIe links at once and rank 0 ends up holding the whole
+    field.  `own` = (first, last) element range this rank writes: it is first-touched here (pages
+    land on this process's NUMA node) and only that range is registered with CUDA.
+    Returns (tensor, path, registered_ptr) or (None, path, None)."""
     import torch
     path = f"/dev/shm/{name}"
     try:
@@ -272,12 +297,18 @@ def shared_pinned(name, count, create):
             with open(path, "wb") as fh:
                 fh.truncate(count * 8)
         t = torch.from_file(path, shared=True, size=count, dtype=torch.float64)
-        rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), count * 8, 0)
+        lo, hi = (0, count) if own is None else (max(0, own[0]), min(count, own[1]))
+        page = 4096 // 8
+        lo, hi = lo // page * page, min(count, -(-hi // page) * page)
+        if hi > lo:
+            t[lo:hi].zero_()                                   # first touch
+        ptr = t.data_ptr() + lo * 8
+        rc = torch.cuda.cudart().cudaHostRegister(ptr, (hi - lo) * 8, 0) if hi > lo else 0
         if int(rc) != 0:
-            return None, path
-        return t, path
+            return None, path, None
+        return t, path, ptr
     except Exception:
-        return None, path
+        return None, path, None
 
 
 def run_b200(args):
@@ -440,23 +471,27 @@ def run_b200(args):
     # block plus one stencil-only halo row per interior edge (recomputed, 2 of nx/N rows), so the
     # end-to-end path needs no exchange at all.
     tag = f"b200cs_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
-    ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, rank == 0) if world == 1 else (None, None)
-    fm_sh, fm_path = (None, None)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
+    # element ranges this rank writes: its FTLE rows; its flow-map rows plus one halo row per interior edge
+    own_ft = (i0 * n, i1 * n)
+    own_fm = ((i0 - has_lo) * 2 * n, (i1 + has_hi) * 2 * n)
     if world > 1:
         if rank == 0:
-            ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, True)
-            fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, True)
+            ft_sh, ft_path, ft_reg = shared_pinned(tag + "_ftle", n * n, True, own_ft)
+            fm_sh, fm_path, fm_reg = shared_pinned(tag + "_fm", 2 * n * n, True, own_fm)
         dist.barrier()
         if rank != 0:
-            ft_sh, ft_path = shared_pinned(tag + "_ftle", n * n, False)
-            fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, False)
+            ft_sh, ft_path, ft_reg = shared_pinned(tag + "_ftle", n * n, False, own_ft)
+            fm_sh, fm_path, fm_reg = shared_pinned(tag + "_fm", 2 * n * n, False, own_fm)
         ok = torch.tensor([int(ft_sh is not None and fm_sh is not None)], device="cuda")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         assembled = bool(int(ok))
     else:
-        fm_sh, fm_path = shared_pinned(tag + "_fm", 2 * n * n, True)
+        ft_sh, ft_path, ft_reg = shared_pinned(tag + "_ftle", n * n, True)
+        fm_sh, fm_path, fm_reg = shared_pinned(tag + "_fm", 2 * n * n, True)
         assembled = ft_sh is not None and fm_sh is not None
     if not assembled:   # no shared memory: every rank keeps its rows in its own pinned buffer
+        ft_reg = fm_reg = None
         ft_sh = torch.empty(n * n if world == 1 else rows * n, dtype=torch.float64).pin_memory()
         fm_sh = torch.empty(2 * (n * n if world == 1 else rows * n), dtype=torch.float64).pin_memory()
     ft_full = ft_sh.view(-1, n)
@@ -585,8 +620,8 @@ def run_b200(args):
     # release the shared host buffers
     try:
         if assembled:
-            torch.cuda.cudart().cudaHostUnregister(ft_sh.data_ptr())
-            torch.cuda.cudart().cudaHostUnregister(fm_sh.data_ptr())
+            torch.cuda.cudart().cudaHostUnregister(ft_reg)
+            torch.cuda.cudart().cudaHostUnregister(fm_reg)
         del ft_full, fm_full, ft_sh, fm_sh
         if world > 1:
             dist.barrier()
@@ -636,7 +671,7 @@ def run_b200(args):
             e2e_entry = {"value": pts / (e2e_fm_ms / K * 1e-3), "unit": "grid points/s", "h2d_bytes_per_step": h2d,
                          "d2h_bytes_per_step": int(24 * pts), "ms_per_step": e2e_fm_ms / K,
                          "assembled_on_rank0_host": True, "planning_inside": world > 1, "result": how,
-                         "ftle_only": ftle_only}
+                         "numa_node_of_rank0": numa_node, "ftle_only": ftle_only}
         else:
             e2e_entry = {"value": e2e_val, "unit": "grid points/s", "h2d_bytes_per_step": h2d,
                          "d2h_bytes_per_step": int(8 * pts), "ms_per_step": e2e_ms / K,
