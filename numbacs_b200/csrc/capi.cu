@@ -166,11 +166,13 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
     }
     if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
     R.coef_uv = nullptr;
+    R.slot = -1;
     R.oog = f.oog;
     R.r = f.r;
     std::memset(&R.grid, 0, sizeof(R.grid));
     if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
         R.grid = make_grid_dev(f);
+        R.grid.oog = f.oog;
         R.coef_uv = static_cast<const double2 *>(f.coef);
     }
 }

@@ -25,6 +25,7 @@ SplineGridDev make_grid_dev(const FlowSpec &f) {
     g.s1 = f.grid.n[2] + pad;
     g.s0 = (long long)(f.grid.n[1] + pad) * g.s1;
     g.extrap = f.extrap;
+    g.oog = nullptr;   // set by fill_rhs for the right-hand sides only (callables and scalars do not count)
     return g;
 }
 

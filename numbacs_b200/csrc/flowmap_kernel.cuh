@@ -54,6 +54,13 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
 #ifndef B200CS_BICKLEY_MINBLOCKS
 #define B200CS_BICKLEY_MINBLOCKS 5
 #endif
+#ifndef B200CS_RHS_SLOTS   // out-of-line RHS reads its parameters from a __constant__ slot: 304 -> 331 M points/s (spline probe)
+#define B200CS_RHS_SLOTS 1
+#endif
+template <class T, class = void>
+struct rhs_out_of_line : std::false_type {};
+template <class T>
+struct rhs_out_of_line<T, std::void_t<decltype(T::kOutOfLine)>> : std::bool_constant<T::kOutOfLine> {};
 #ifndef B200CS_BICKLEY_KSMEM
 #define B200CS_BICKLEY_KSMEM false
 #endif
@@ -328,12 +335,41 @@ void launch_lavd_one(const IntegArgs &A, cudaStream_t s) {
     B2_CHECK_CUDA(cudaGetLastError());
 }
 
+// One __constant__ parameter slot per stream (c_rhs_slots, flows.cuh): launches on one stream are
+// ordered, so re-writing the stream's slot before a launch cannot disturb an earlier kernel; two
+// streams never share a slot until more than kRhsSlots distinct streams have been seen, at which
+// point the device is drained once before the table is reused.
+inline int rhs_slot_for_stream(cudaStream_t s) {
+    static std::mutex mu;
+    static std::vector<cudaStream_t> seen;
+    std::lock_guard<std::mutex> lk(mu);
+    for (size_t k = 0; k < seen.size(); ++k)
+        if (seen[k] == s) return (int)k;
+    if ((int)seen.size() == kRhsSlots) {
+        cudaDeviceSynchronize();
+        seen.clear();
+    }
+    seen.push_back(s);
+    return (int)seen.size() - 1;
+}
+
 template <class Rhs, bool DENSE, int MODE>
 void launch_one(const IntegArgs &A, cudaStream_t s) {
     constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
     const long long blocks = (A.npts + kBlock - 1) / kBlock;
     if (blocks <= 0) return;
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
+#if B200CS_RHS_SLOTS
+    if constexpr (rhs_out_of_line<Rhs>::value) {   // the flows with an out-of-line RHS (spline / linear)
+        IntegArgs B = A;
+        B.rhs.slot = rhs_slot_for_stream(s);
+        B2_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_rhs_slots, &B.rhs, sizeof(RhsParams), sizeof(RhsParams) * B.rhs.slot,
+                                              cudaMemcpyHostToDevice, s));
+        flowmap_kernel<Rhs, DENSE, MODE><<<(unsigned)blocks, kBlock, 0, s>>>(B);
+        B2_CHECK_CUDA(cudaGetLastError());
+        return;
+    }
+#endif
     flowmap_kernel<Rhs, DENSE, MODE><<<(unsigned)blocks, kBlock, 0, s>>>(A);
     B2_CHECK_CUDA(cudaGetLastError());
 }

@@ -34,7 +34,16 @@ struct RhsParams {
     double d[8];              // constants derived from p on the host (fill_rhs, capi.cu)
     double e[9];              // double gyre: eps * (sinpi polynomial coefficients cp[0..7], pi)
     unsigned long long *oog;  // Spline2D: out-of-grid evaluation counter of the flow (may be null)
+    int slot;                 // >= 0: a copy of this struct sits in c_rhs_slots[slot] (out-of-line RHS)
 };
+
+// Parameter blocks for the out-of-line right-hand sides.  A __noinline__ device function cannot
+// name its caller's kernel parameters, and reading them through a generic pointer turns ~25
+// constant-bank operands per spline RHS into LD.E loads on the same LSU pipe that carries the 64
+// coefficient taps.  The launcher copies the block into a __constant__ slot (one slot per stream,
+// flowmap_kernel.cuh) and the out-of-line function indexes it: uniform constant loads again.
+constexpr int kRhsSlots = 32;
+static __constant__ RhsParams c_rhs_slots[kRhsSlots];
 
 #ifndef B200CS_BICKLEY_WIDE
 #define B200CS_BICKLEY_WIDE 1
@@ -213,6 +222,7 @@ using DoubleGyreDamped = DoubleGyreT<true>;
 struct BickleyJet {
     static constexpr int N = 2;
     static constexpr int kAux = 0;
+    static constexpr bool kOutOfLine = B200CS_BICKLEY_NOINLINE != 0;
     const RhsParams &P;
     __device__ __forceinline__ explicit BickleyJet(const RhsParams &P_) : P(P_) {}
     template <int M>
@@ -229,8 +239,15 @@ struct BickleyJet {
         self.eval_body(t, y, dy);
         return make_double2(dy[0], dy[1]);
     }
+    static __device__ __noinline__ double2 eval_ool_slot(int slot, double t, double y0, double y1) {
+        const BickleyJet self(c_rhs_slots[slot]);
+        const double y[2] = {y0, y1};
+        double dy[2];
+        self.eval_body(t, y, dy);
+        return make_double2(dy[0], dy[1]);
+    }
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
-        const double2 r = eval_ool(&P, t, y[0], y[1]);
+        const double2 r = (P.slot >= 0) ? eval_ool_slot(P.slot, t, y[0], y[1]) : eval_ool(&P, t, y[0], y[1]);
         dy[0] = r.x;
         dy[1] = r.y;
     }
@@ -359,6 +376,7 @@ template <int SPHERICAL, bool LINEAR = false>
 struct Spline2D {
     static constexpr int N = 2;
     static constexpr int kAux = 0;
+    static constexpr bool kOutOfLine = B200CS_SPLINE_NOINLINE != 0;
     const RhsParams &P;
     __device__ __forceinline__ explicit Spline2D(const RhsParams &P_) : P(P_) {}
     template <int M>
@@ -374,8 +392,15 @@ struct Spline2D {
         self.eval_body(t, y, dy);
         return make_double2(dy[0], dy[1]);
     }
+    static __device__ __noinline__ double2 eval_ool_slot(int slot, double t, double y0, double y1) {
+        const Spline2D self(c_rhs_slots[slot]);
+        const double y[2] = {y0, y1};
+        double dy[2];
+        self.eval_body(t, y, dy);
+        return make_double2(dy[0], dy[1]);
+    }
     __device__ __forceinline__ void eval(double, double t, const double (&y)[2], double (&dy)[2]) const {
-        const double2 r = eval_ool(&P, t, y[0], y[1]);
+        const double2 r = (P.slot >= 0) ? eval_ool_slot(P.slot, t, y[0], y[1]) : eval_ool(&P, t, y[0], y[1]);
         dy[0] = r.x;
         dy[1] = r.y;
     }
@@ -392,12 +417,8 @@ struct Spline2D {
         if (SPHERICAL == 2) xx = pymod_pos(y[0], 360.0);
         double u, v;
         const double tt = p0 * t;
-        // count evaluations outside the data grid (the only guard on the extrapolation
-        // modes, which no reference test pins); a particle that stays inside never takes the branch
-        if (tt < P.grid.a[0] || tt > P.grid.b[0] || xx < P.grid.a[1] || xx > P.grid.b[1] || yy < P.grid.a[2] ||
-            yy > P.grid.b[2]) {
-            if (P.oog) atomicAdd(P.oog, 1ULL);
-        }
+        // evaluations outside the data grid are counted inside the evaluators (spline.cuh, count_outside):
+        // the only guard on the extrapolation modes, which no reference test pins
         if (LINEAR) eval_linear_uv(P.grid, P.coef_uv, tt, xx, yy, u, v);
         else eval_spline_uv(P.grid, P.coef_uv, tt, xx, yy, u, v);
         if (SPHERICAL) {

@@ -31,7 +31,19 @@ struct SplineGridDev {
     int n[3];         // data points per axis
     long long s0, s1; // element strides of axes 0 and 1 of the coefficient array
     int extrap;       // B200CS_EXTRAP_*
+    unsigned long long *oog;  // velocity fields: counter of evaluations outside the data grid (may be null)
 };
+
+// Out-of-grid bookkeeping on the integer pipe (the FP64 pipe is what these kernels are short of): a
+// local coordinate lam in [0, 1] has a high word in [0, 0x3ff00000]; anything negative (sign bit) or
+// above 1 compares greater as an unsigned.  (lam within 2^-20 above 1 passes as inside: a millionth
+// of a cell.)
+__device__ __forceinline__ bool lam_outside(double lam) {
+    return (unsigned)__double2hiint(lam) > 0x3ff00000u;
+}
+__device__ __forceinline__ void count_outside(const SplineGridDev &g, bool outside) {
+    if (outside && g.oog) atomicAdd(g.oog, 1ULL);
+}
 
 // cell index and local coordinate:  i = clamp(floor((x-a)/delta), 0, n-2),  lam = ((x-a) - i*delta)/delta
 // (the product i*delta is rounded before the subtraction, as in unfused CPU arithmetic)
@@ -128,12 +140,18 @@ __device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const dou
                                                double t, double x, double y, double &u, double &v) {
     u = 0.0;
     v = 0.0;
-    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return;
+    const double t_in = t, x_in = x, y_in = y;
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) {
+        count_outside(g, true);
+        return;
+    }
     int i0, i1, i2;
     double l0, l1, l2;
     axis_locate(g, 0, t, i0, l0);
     axis_locate(g, 1, x, i1, l1);
     axis_locate(g, 2, y, i2, l2);
+    if (g.extrap == B200CS_EXTRAP_NEAREST) count_outside(g, t != t_in || x != x_in || y != y_in);   // clamped
+    else count_outside(g, lam_outside(l0) || lam_outside(l1) || lam_outside(l2));
     const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
     double P0[4], P1[4], P2[4];
     bspline_weights(l0, lin, P0);
@@ -197,12 +215,18 @@ __device__ __forceinline__ void eval_linear_uv(const SplineGridDev &g, const dou
                                                double t, double x, double y, double &u, double &v) {
     u = 0.0;
     v = 0.0;
-    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return;
+    const double t_in = t, x_in = x, y_in = y;
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) {
+        count_outside(g, true);
+        return;
+    }
     int i0, i1, i2;
     double l0, l1, l2;
     axis_locate(g, 0, t, i0, l0);
     axis_locate(g, 1, x, i1, l1);
     axis_locate(g, 2, y, i2, l2);
+    if (g.extrap == B200CS_EXTRAP_NEAREST) count_outside(g, t != t_in || x != x_in || y != y_in);   // clamped
+    else count_outside(g, lam_outside(l0) || lam_outside(l1) || lam_outside(l2));
     const double2 *c = F + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
     const double m2 = 1.0 - l2;
 #pragma unroll

@@ -29,6 +29,6 @@ for _ in range(reps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 n = x.numel() * y.numel()
-st = np.asarray(info["stats"], dtype=np.float64)
+st = np.asarray(info["stats"].cpu() if hasattr(info["stats"], "cpu") else info["stats"], dtype=np.float64)
 print(f"bickley {x.numel()} x {y.numel()}: {min(ts):.3f} ms = {n / min(ts) / 1e3:.1f} M points/s; "
       f"attempts/particle {(st[1] + st[2]) / n:.2f}, nfev/particle {st[0] / n:.1f}")
