@@ -70,6 +70,9 @@
 #ifndef B200CS_CTRL_FAST
 #define B200CS_CTRL_FAST (!B200CS_STRICT_INT)
 #endif
+#ifndef B200CS_FSAL_ALWAYS
+#define B200CS_FSAL_ALWAYS 0
+#endif
 #ifndef B200CS_SYNC_EVERY
 #define B200CS_SYNC_EVERY 8
 #endif
@@ -419,10 +422,15 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         const double fac = fmax(kFacc2, fmin(kFacc1, fac11s));  // beta = 0
         double hnew = h / fac;
 #endif
+#if B200CS_FSAL_ALWAYS
+        detail::eval_to(rhs, aux[12], xph, y5, K, 13);  // A/B: FSAL slope evaluated before the accept test
+#endif
         if (err <= 1.0) {
             // ---- accepted
             ++cnt.accepted;
+#if !B200CS_FSAL_ALWAYS
             detail::eval_to(rhs, aux[12], xph, y5, K, 13);  // first-same-as-last slope, same time as stage 12
+#endif
             if (DENSE) {
                 if (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0) {
                     ++cnt.dense;

@@ -243,8 +243,16 @@ __device__ __forceinline__ bool sinpi_in_range(double u) {
 // arguments (tools/fit_trig_poly.py): max error 2.96 ulp / 3.3e-16 absolute, against 2.33 ulp for
 // the split form and 1.4e-15 absolute for the reference's own sin(pi*x) with |x| < 4, whose
 // argument pi*x is rounded before libm sees it.
+// B200CS_SINPI_NOBRANCH (round 2, default): no libm fall-back branch in the sin(pi u) kernels.  The
+// guard is not needed for correctness (see below) and without it a whole step attempt of the
+// double-gyre kernel is a handful of basic blocks that ptxas schedules as one: 705 -> 311 non-FP64
+// instructions in the attempt loop, 1060 -> 1103 M points/s at 8192^2 (profiles/r2_ab_dg_nobranch.txt).
+#ifndef B200CS_SINPI_NOBRANCH
+#define B200CS_SINPI_NOBRANCH 1
+#endif
 template <int M>
 __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) {
+#if !B200CS_SINPI_NOBRANCH
     bool slow = false;
 #pragma unroll
     for (int m = 0; m < M; ++m) slow |= !sinpi_in_range(u[m]);
@@ -253,6 +261,9 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
         for (int m = 0; m < M; ++m) s[m] = sincos_slow(3.141592653589793 * u[m]).x;
         return;
     }
+#endif
+    // (without the guard the fast path is still right at the edges: NaN and inf propagate to NaN
+    //  through u - (t - magic); a finite |u| >= 2^52 is an integer and gives r = 0, i.e. +-0)
     int q[M];
     double r[M], z[M], p[M];
 #pragma unroll
@@ -279,6 +290,7 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
 // the rounding of the product amp * sin it replaces).
 template <int M>
 __device__ __forceinline__ void sinpi12_scaled_v(const double (&u)[M], double (&s)[M], const double (&ce)[9]) {
+#if !B200CS_SINPI_NOBRANCH
     bool slow = false;
 #pragma unroll
     for (int m = 0; m < M; ++m) slow |= !sinpi_in_range(u[m]);
@@ -288,6 +300,7 @@ __device__ __forceinline__ void sinpi12_scaled_v(const double (&u)[M], double (&
         for (int m = 0; m < M; ++m) s[m] = amp * sincos_slow(3.141592653589793 * u[m]).x;
         return;
     }
+#endif
     int q[M];
     double r[M], z[M], p[M];
 #pragma unroll

@@ -17,9 +17,10 @@ namespace b200cs {
 namespace {
 
 // Launch shape per (flow, output mode).  Default: 128-thread blocks, as many as the registers allow.
-// The double-gyre kernels (the headline workload) pin that to six blocks per SM (80 registers, no
-// spills since the round-2 RHS / controller trims; five blocks at 96 registers before: 1056.6 vs
-// 1062.4 M points/s at 8192^2, profiles/r2_ab_dg.txt): their attempt loop fits the 32 KB L1.5 instruction cache, so free-running small
+// The double-gyre kernels (the headline workload) pin that to five blocks per SM (96 registers): with
+// the guarded sines six blocks at 80 registers were 0.5 % ahead (profiles/r2_ab_dg.txt), with the
+// branch-free sines the larger basic blocks want the registers (1103 vs 1082 M points/s at 8192^2,
+// profiles/r2_ab_dg_nobranch.txt).  Their attempt loop fits the 32 KB L1.5 instruction cache, so free-running small
 // blocks beat every lockstep shape (profiles/r1c_ab_variants_a.txt: 640-thread lockstep 879,
 // 2 x 384 lockstep 907, free 128 x 5 / 192 x 4 / 256 x 3 / 64 x 12 all 915-917 M points/s at 8192^2).
 // The spline kernels gain 32 % from LOCKSTEP -- one 512-thread block per SM whose warps meet at a
@@ -39,7 +40,7 @@ struct KernelShape {
 #define B200CS_DG_LOCKSTEP false
 #endif
 #ifndef B200CS_DG_MINBLOCKS
-#define B200CS_DG_MINBLOCKS 6
+#define B200CS_DG_MINBLOCKS 5
 #endif
 template <bool DAMPED>
 struct KernelShape<DoubleGyreT<DAMPED>, false> {

@@ -176,7 +176,9 @@ struct DoubleGyreT {
     // a kernel that is FP64-issue bound.  The identity is exact; the rounding differs from the
     // reference's product form by a few 1e-16 in ABSOLUTE terms (the same size as libm-vs-libm
     // differences), both forms vanish exactly on the walls x = 0 and y = 0, and the parity tests
-    // (step-count equality, 1e-8 x domain) are the guard.
+    // (step-count equality, 1e-8 x domain) are the guard.  (Forming S+ + S- and S+ - S- as FMAs on
+    // r1 Q1 would save one more instruction but leaves the rounding residual of r Q on the walls,
+    // where the reference's velocity component is an exact 0: not done.)
     __device__ __forceinline__ void eval(double a, double /*t*/, const double (&y)[2], double (&dy)[2]) const {
         const double c = P.d[1];     // p0 * pi*A/2 (exact scalings of pi*A)
         const double b = 1.0 - 2.0 * a;
