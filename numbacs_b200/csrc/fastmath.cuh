@@ -358,6 +358,7 @@ __device__ __forceinline__ void sin_wide_v(const double (&x)[M], double (&s)[M])
 // the parity selects of sincos_fast.  cos is evaluated as 1 + z Pc(z): its ABSOLUTE error is
 // ~2e-16 everywhere, its relative error grows near the zeros of cos (the flows multiply it by an
 // O(1) amplitude and add it to O(1) terms, so absolute accuracy is what matters there).
+__device__ __forceinline__ void sincos_wide_core(double x, double *s, double *c);
 __device__ __forceinline__ void sincos_wide(double x, double *s, double *c) {
     if (!trig_in_range(x)) {
         const double2 sc = sincos_slow(x);
@@ -365,6 +366,10 @@ __device__ __forceinline__ void sincos_wide(double x, double *s, double *c) {
         *c = sc.y;
         return;
     }
+    sincos_wide_core(x, s, c);
+}
+// the unguarded kernel: the caller has checked |x| < 1e5 (one test for all the arguments of a RHS)
+__device__ __forceinline__ void sincos_wide_core(double x, double *s, double *c) {
     const double t = fma(x, kWide.inv_pi, kWide.magic);
     const int q = __double2loint(t);
     const double k = t - kWide.magic;

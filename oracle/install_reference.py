@@ -25,9 +25,16 @@ def install(force=False):
     if os.path.isdir(DST) and not force:
         return DST
     if os.path.isdir(DST):
+        for root, dirs, files in os.walk(DST):
+            for name in dirs:
+                os.chmod(os.path.join(root, name), 0o755)
         shutil.rmtree(DST)
     os.makedirs(os.path.dirname(DST), exist_ok=True)
     shutil.copytree(SRC, DST, ignore=shutil.ignore_patterns("__pycache__"))
+    for root, dirs, files in os.walk(os.path.dirname(DST)):     # the source tree is read-only; the copy is not
+        for name in dirs + files:
+            pth = os.path.join(root, name)
+            os.chmod(pth, os.stat(pth).st_mode | 0o200)
     return DST
 
 
