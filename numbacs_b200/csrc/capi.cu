@@ -165,6 +165,10 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
         R.e[8] = R.p[2] * 3.141592653589793;
     }
     if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
+    if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
+        R.d[7] = 3.141592653589793 * f.r;   // pi r, the divisor of the spherical v component (flows.py:180)
+        R.d[6] = 1.0 / R.d[7];
+    }
     R.coef_uv = nullptr;
     R.slot = -1;
     R.oog = f.oog;

@@ -54,6 +54,9 @@ static __constant__ RhsParams c_rhs_slots[kRhsSlots];
 #ifndef B200CS_DG_TRIM      // round 2: eps folded into the sinpi coefficients of a(t), f / df without 2a
 #define B200CS_DG_TRIM 1
 #endif
+#ifndef B200CS_SPLINE_LEAN_SPH   // spherical tail of the spline RHS without fmod / IEEE-division slow paths
+#define B200CS_SPLINE_LEAN_SPH 1
+#endif
 #ifndef B200CS_SPLINE_NOINLINE
 #define B200CS_SPLINE_NOINLINE 1
 #endif
@@ -399,6 +402,34 @@ __device__ __forceinline__ double pymod_pos(double a, double m) {
     return r;
 }
 
+// a % 360 (Python semantics) without fmod's loop and branches: k = rint(a / 360) by the magic
+// constant, r = a - 360 k EXACTLY (one FMA: the exact remainder of a by 360 is representable), in
+// [-180, 180], and a negative r moves up by 360 -- the same final addition (and the same rounding of
+// it, e.g. -1e-20 % 360 == 360.0) as Python's fmod-then-adjust.  |a| >= 2^40 or non-finite: fmod.
+__device__ __forceinline__ double pymod360(double a) {
+    if (!(fabs(a) < 1.0e12)) return pymod_pos(a, 360.0);
+    const double t = fma(a, 1.0 / 360.0, 6755399441055744.0);
+    const double k = t - 6755399441055744.0;
+    double r = fma(-360.0, k, a);
+    // a / 360 within rounding of a half-integer can leave |r| a hair above 180: still exact, still in (-360, 360)
+    if (r < 0.0) r += 360.0;
+    return r;
+}
+
+// cos(x) with the wide kernel (one reduction by pi, even polynomial on |r| <= pi/2), no libm guard:
+// the caller passes a latitude in radians
+__device__ __forceinline__ double cos_wide_core(double x) {
+    const double t = fma(x, kWide.inv_pi, kWide.magic);
+    const int q = __double2loint(t);
+    const double k = t - kWide.magic;
+    const double r = fma(-k, kWide.pi_lo, fma(-k, kWide.pi_hi, x));
+    const double z = r * r;
+    double pc = kWide.cc[7];
+#pragma unroll
+    for (int j = 6; j >= 0; --j) pc = fma(pc, z, kWide.cc[j]);
+    return flip_sign(fma(z, pc, 1.0), q & 1);
+}
+
 // LINEAR = true: get_flow_linear_2D (flows.py:418-506), trilinear eval_linear on the raw (u, v)
 // data instead of the tri-cubic spline; everything else (longitude wrap, spherical scaling) is
 // the same expression in the reference.
@@ -443,8 +474,13 @@ struct Spline2D {
         const double p0 = P.p[0];
         double xx = y[0];
         const double yy = y[1];
+#if B200CS_SPLINE_LEAN_SPH && !B200CS_STRICT_RHS
+        if (SPHERICAL == 1) xx = pymod360(y[0] - 180.0) - 180.0;
+        if (SPHERICAL == 2) xx = pymod360(y[0]);
+#else
         if (SPHERICAL == 1) xx = pymod_pos(y[0] - 180.0, 360.0) - 180.0;
         if (SPHERICAL == 2) xx = pymod_pos(y[0], 360.0);
+#endif
         double u, v;
         const double tt = p0 * t;
         // evaluations outside the data grid are counted inside the evaluators (spline.cuh, count_outside):
@@ -455,10 +491,30 @@ struct Spline2D {
             // ((p0*u)*180) / (pi*r*cos(yy*pi/180))   (flows.py:165-196)
 #if B200CS_STRICT_RHS
             dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos(yy * kPi / 180.0));
+            dy[1] = ((p0 * v) * 180.0) / (kPi * P.r);
+#elif B200CS_SPLINE_LEAN_SPH
+            // the same expressions with the divisions as reciprocal + one FMA residual correction (the
+            // quotient to <= 1 ulp, no slow-path branch) and the cosine from the wide kernel; the
+            // latitude argument yy*pi/180 keeps the reference's two roundings
+            const double ypi = yy * kPi;
+            const double ql = ypi * (1.0 / 180.0);
+            const double lat = fma(fma(-ql, 180.0, ypi), 1.0 / 180.0, ql);   // (yy*pi)/180, correctly rounded
+            const double cl = (fabs(lat) < 1.0e5) ? cos_wide_core(lat) : cos(lat);
+            const double den = kPi * P.r * cl;
+            double rd;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rd) : "d"(den));
+            rd = fma(rd, fma(-den, rd, 1.0), rd);
+            rd = fma(rd, fma(-den, rd, 1.0), rd);
+            const double nu = (p0 * u) * 180.0;
+            const double qu = nu * rd;
+            dy[0] = fma(fma(-qu, den, nu), rd, qu);
+            const double nv = (p0 * v) * 180.0;
+            const double qv = nv * P.d[6];                 // 1 / (pi r), from the host
+            dy[1] = fma(fma(-qv, P.d[7], nv), P.d[6], qv);  // P.d[7] = pi r
 #else
             dy[0] = ((p0 * u) * 180.0) / (kPi * P.r * cos_fast(yy * kPi / 180.0));
-#endif
             dy[1] = ((p0 * v) * 180.0) / (kPi * P.r);
+#endif
         } else {
             dy[0] = p0 * u;
             dy[1] = p0 * v;

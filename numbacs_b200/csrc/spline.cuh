@@ -15,7 +15,7 @@
 #define B200CS_STRICT 0
 #endif
 #ifndef B200CS_LOCATE_MAGIC
-#define B200CS_LOCATE_MAGIC 0
+#define B200CS_LOCATE_MAGIC 1
 #endif
 #ifndef B200CS_STRICT_RHS   // the right-hand-side half of the strict build on its own (A/B decomposition)
 #define B200CS_STRICT_RHS B200CS_STRICT
@@ -34,12 +34,11 @@ struct SplineGridDev {
     unsigned long long *oog;  // velocity fields: counter of evaluations outside the data grid (may be null)
 };
 
-// Out-of-grid bookkeeping on the integer pipe (the FP64 pipe is what these kernels are short of): a
-// local coordinate lam in [0, 1] has a high word in [0, 0x3ff00000]; anything negative (sign bit) or
-// above 1 compares greater as an unsigned.  (lam within 2^-20 above 1 passes as inside: a millionth
-// of a cell.)
+// Out-of-grid test on the integer pipe (the FP64 pipe is what these kernels are short of): the bit
+// pattern of a local coordinate lam in [+0, 1] is at most 0x3ff0000000000000; anything above 1,
+// negative (sign bit set, -0 included) or NaN compares greater as an unsigned 64-bit integer.
 __device__ __forceinline__ bool lam_outside(double lam) {
-    return (unsigned)__double2hiint(lam) > 0x3ff00000u;
+    return (unsigned long long)__double_as_longlong(lam) > 0x3ff0000000000000ULL;
 }
 __device__ __forceinline__ void count_outside(const SplineGridDev &g, bool outside) {
     if (outside && g.oog) atomicAdd(g.oog, 1ULL);
@@ -135,28 +134,24 @@ __device__ __forceinline__ bool extrap_coord(const SplineGridDev &g, int d, doub
     return true;
 }
 
-// 64-tap tri-cubic evaluation of an interleaved (u, v) field.
-__device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const double2 *__restrict__ C,
-                                               double t, double x, double y, double &u, double &v) {
-    u = 0.0;
-    v = 0.0;
-    const double t_in = t, x_in = x, y_in = y;
-    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) {
-        count_outside(g, true);
-        return;
-    }
-    int i0, i1, i2;
-    double l0, l1, l2;
-    axis_locate(g, 0, t, i0, l0);
-    axis_locate(g, 1, x, i1, l1);
-    axis_locate(g, 2, y, i2, l2);
-    if (g.extrap == B200CS_EXTRAP_NEAREST) count_outside(g, t != t_in || x != x_in || y != y_in);   // clamped
-    else count_outside(g, lam_outside(l0) || lam_outside(l1) || lam_outside(l2));
-    const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
-    double P0[4], P1[4], P2[4];
-    bspline_weights(l0, lin, P0);
-    bspline_weights(l1, lin, P1);
-    bspline_weights(l2, lin, P2);
+// cubic weights for a local coordinate inside [0, 1] (no extrapolation cases, no branches)
+__device__ __forceinline__ void bspline_weights_in(double l, double (&P)[4]) {
+#if B200CS_STRICT_RHS
+    bspline_weights(l, false, P);
+#else
+    const double s = 1.0 / 6.0;
+    const double l2 = l * l, l3 = l2 * l;
+    P[0] = sp_mad(-s, l3, sp_mad(0.5, l2, sp_mad(-0.5, l, s)));
+    P[1] = sp_mad(0.5, l3, sp_mad(-1.0, l2, 4.0 * s));
+    P[2] = sp_mad(-0.5, l3, sp_mad(0.5, l2, sp_mad(0.5, l, s)));
+    P[3] = s * l3;
+#endif
+}
+
+// the 64 taps: nested t -> x -> y sum of an interleaved (u, v) field
+__device__ __forceinline__ void spline_taps_uv(const SplineGridDev &g, const double2 *__restrict__ C, int i0, int i1,
+                                               int i2, const double (&P0)[4], const double (&P1)[4],
+                                               const double (&P2)[4], double &u, double &v) {
     const double2 *base = C + (long long)i0 * g.s0 + (long long)i1 * g.s1 + i2;
     double au = 0.0, av = 0.0;
 #pragma unroll
@@ -176,6 +171,58 @@ __device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const dou
     }
     u = au;
     v = av;
+}
+
+// the general path: a point outside the data grid, every extrapolation mode (rare; out of line so
+// that the common path below stays one basic block)
+static __device__ __noinline__ double2 eval_spline_uv_outside(const SplineGridDev *gp, const double2 *__restrict__ C,
+                                                              double t, double x, double y) {
+    const SplineGridDev &g = *gp;
+    count_outside(g, true);
+    if (!extrap_coord(g, 0, t) || !extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return make_double2(0.0, 0.0);
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
+    double P0[4], P1[4], P2[4];
+    bspline_weights(l0, lin, P0);
+    bspline_weights(l1, lin, P1);
+    bspline_weights(l2, lin, P2);
+    double u, v;
+    spline_taps_uv(g, C, i0, i1, i2, P0, P1, P2, u, v);
+    return make_double2(u, v);
+}
+
+// 64-tap tri-cubic evaluation of an interleaved (u, v) field.  Common path (the point is inside the
+// grid, whatever the extrapolation mode): locate, ONE integer test of the three local coordinates,
+// cubic weights, taps.  A point outside takes the out-of-line general path above.
+__device__ __forceinline__ void eval_spline_uv(const SplineGridDev &g, const double2 *__restrict__ C,
+                                               double t, double x, double y, double &u, double &v) {
+    int i0, i1, i2;
+    double l0, l1, l2;
+    axis_locate(g, 0, t, i0, l0);
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    // NaN coordinates: lam is NaN, its bit pattern compares greater -> general path -> NaN / 0 as before
+    bool outside = lam_outside(l0) || lam_outside(l1) || lam_outside(l2);
+    // 'constant' and 'nearest' are defined on the coordinates themselves (a point one ulp beyond the
+    // last node is outside even if its local coordinate rounds to 1): the exact comparisons, taken
+    // only in those modes ('linear' continues the cubic weights, so lam decides)
+    if (g.extrap != B200CS_EXTRAP_LINEAR)
+        outside = outside || t < g.a[0] || t > g.b[0] || x < g.a[1] || x > g.b[1] || y < g.a[2] || y > g.b[2];
+    if (outside) {
+        const double2 r = eval_spline_uv_outside(&g, C, t, x, y);
+        u = r.x;
+        v = r.y;
+        return;
+    }
+    double P0[4], P1[4], P2[4];
+    bspline_weights_in(l0, P0);
+    bspline_weights_in(l1, P1);
+    bspline_weights_in(l2, P2);
+    spline_taps_uv(g, C, i0, i1, i2, P0, P1, P2, u, v);
 }
 
 // scalar tri-cubic
