@@ -152,6 +152,7 @@ static void read_params(const double *params, int nparams, int min_params, RhsPa
 static void fill_rhs(const FlowSpec &f, RhsParams &R) {
     for (double &d : R.d) d = 0.0;
     for (double &d : R.e) d = 0.0;
+    for (double &d : R.e2) d = 0.0;
     if (f.kind == B200CS_FLOW_DOUBLE_GYRE) {
         // constants of the double-gyre RHS folded once here (the same IEEE operations the kernel
         // used to repeat in every stage): see DoubleGyreT in flows.cuh
@@ -163,6 +164,8 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
         // eps folded into the sinpi polynomial of a(t) = eps sin(pi u) (sinpi12_scaled_v, fastmath.cuh)
         for (int k = 0; k < 8; ++k) R.e[k] = R.p[2] * kSinPiCpHost[k];
         R.e[8] = R.p[2] * 3.141592653589793;
+        for (int k = 0; k < 8; ++k) R.e2[k] = R.d[1] * kSinPiCpHost[k];   // amplitude of S+ / S- folded the same way
+        R.e2[8] = R.d[1] * 3.141592653589793;
     }
     if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
     if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
