@@ -167,7 +167,22 @@ static void fill_rhs(const FlowSpec &f, RhsParams &R) {
         for (int k = 0; k < 8; ++k) R.e2[k] = R.d[1] * kSinPiCpHost[k];   // amplitude of S+ / S- folded the same way
         R.e2[8] = R.d[1] * 3.141592653589793;
     }
-    if (f.kind == B200CS_FLOW_BICKLEY_JET) R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
+    if (f.kind == B200CS_FLOW_BICKLEY_JET) {
+#if B200CS_BICKLEY_FOLDED
+        // BickleyJet::eval_body, folded form (flows.cuh): every product of launch constants once, here
+        const double p0 = R.p[0], U0 = R.p[1], L = R.p[2];
+        R.d[7] = 0.5 * L;
+        R.d[5] = 1.0 / R.d[7];                              // 2 / L: 2 Y = y1 * d[5], corrected with d[7]
+        R.d[6] = 4.0 * (p0 * U0);
+        for (int n = 0; n < 3; ++n) {
+            R.e[n] = -(p0 * R.p[9 + n]);                    // -p0 c_n
+            R.e[3 + n] = 2.0 * R.p[3 + n];                  // 2 A_n
+            R.e[6 + n] = -(L * (R.p[3 + n] * R.p[6 + n]));  // -L A_n k_n
+        }
+#else
+        R.d[5] = 1.0 / R.p[2];  // 1 / L_y (BickleyJet::eval)
+#endif
+    }
     if (f.kind == B200CS_FLOW_SPLINE2D || f.kind == B200CS_FLOW_LINEAR2D) {
         R.d[7] = 3.141592653589793 * f.r;   // pi r, the divisor of the spherical v component (flows.py:180)
         R.d[6] = 1.0 / R.d[7];

@@ -73,6 +73,12 @@
 #ifndef B200CS_FSAL_ALWAYS
 #define B200CS_FSAL_ALWAYS 0
 #endif
+// B200CS_HINIT_FAST (round 2, last session): hinit with the controller's reciprocal / rsqrt kernels
+// instead of nine IEEE divisions and three IEEE square roots per particle: +0.7 % on the double
+// gyre at 8192^2 with identical config-1 parity figures (profiles/r3_ab_tile_hinit.txt).
+#ifndef B200CS_HINIT_FAST
+#define B200CS_HINIT_FAST (B200CS_CTRL_FAST && B200CS_LEAN2)
+#endif
 #ifndef B200CS_SYNC_EVERY
 #define B200CS_SYNC_EVERY 8
 #endif
@@ -248,45 +254,50 @@ struct NoSink {
     __device__ __forceinline__ void operator()(int, const double (&)[N]) const {}
 };
 
-// Integrates dy/ds = rhs(s, y) from s = x0 to s = xend.
-//   n_out  == 0 : only the final state is wanted (DENSE must be false)
-//   n_out  >= 2 : output times are t_k = p0 * (t0 + k*step), k = 0..n_out-1 (last = p0*(t0+T)),
-//                 rows 1..n_out-1 go to `sink`
-// Returns B200CS_ST_OK / _NMAX / _HSMALL; y holds the state reached.
-template <bool DENSE, bool LOCKSTEP, class Rhs, int N, class Sink, class KS>
-__device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, double (&y)[N], double x0, double xend,
-                                                double rtol, double atol, int n_out, double out_p0,
-                                                double out_t0, double out_step, Sink &&sink,
-                                                StepCounts &cnt, KS K) {
-    constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
-    constexpr int kNmax = 100000;
-    constexpr int kSyncEvery = B200CS_SYNC_EVERY;
-    // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages (registers or shared memory)
-    double aux[17];   // time-only part of the RHS per stage (flows that have one)
-    double x = x0;
-    const double posneg = (xend - x0) < 0.0 ? -1.0 : 1.0;
-    const double hmax = fabs(xend - x0);
-    bool last = false, reject = false;
-    int nstep = 0;
-    int iout = 1;  // next output row
-    // output time of row k, bit-identical to params[0]*np.linspace(t0, t0+T, n)[k]
-    auto t_out = [&](int k) { return __dmul_rn(out_p0, __dadd_rn(out_t0, __dmul_rn((double)k, out_step))); };
-    double tnext = 0.0;
-    if (DENSE) tnext = t_out(1);
-    // LOCKSTEP: every thread of the block calls this function (inactive ones idle) and the block
-    // meets at a barrier before each step attempt, so all its warps walk the large unrolled body
-    // together and share its instruction-cache footprint.
-    bool alive = active;
-    double h = 0.0;
-    int status = active ? B200CS_ST_OK : B200CS_ST_MASKED;
-
-    if (alive) {
+// First slope K[1] = f(x, y) and the initial step size of Hairer's hinit (iord = 8); returns h.
+template <class Rhs, int N, class KS>
+__device__ __forceinline__ double dop853_start(const Rhs &rhs, double x, const double (&y)[N], double rtol,
+                                               double atol, double hmax, double posneg, KS &K) {
+    double h;
     {
         double t1[1] = {x}, a1[1] = {0.0};
         if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
         detail::eval_to(rhs, a1[0], x, y, K, 1);
     }
     // ---- hinit (iord = 8)
+#if B200CS_HINIT_FAST
+    {   // the same formulas with the controller's reciprocal / rsqrt kernels instead of nine IEEE
+        // divisions and three IEEE square roots (once per particle, ~1 % of its FP64 instructions);
+        // NaN inputs end in h = +-hmax exactly as with the IEEE operations (fmin drops the NaN)
+        double dnf = 0.0, dny = 0.0, rsk[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            rsk[i] = detail::rcp_fast(detail::mad(rtol, fabs(y[i]), atol));
+            const double a = K[1][i] * rsk[i], b = y[i] * rsk[i];
+            dnf = detail::mad(a, a, dnf);
+            dny = detail::mad(b, b, dny);
+        }
+        h = (dnf <= 1.0e-10 || dny <= 1.0e-10) ? 1.0e-6 : detail::sqrt_fast(dny * detail::rcp_fast(dnf)) * 0.01;
+        h = fmin(h, hmax) * posneg;
+        double y1[N], f1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = detail::mad(h, K[1][i], y[i]);
+        double t1[1] = {x + h}, a1[1] = {0.0};
+        if constexpr (Rhs::kAux != 0) rhs.template time_part<1>(t1, a1);
+        rhs.eval(a1[0], x + h, y1, f1);
+        double der2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double a = (f1[i] - K[1][i]) * rsk[i];
+            der2 = detail::mad(a, a, der2);
+        }
+        der2 = detail::sqrt_fast(der2) * detail::rcp_fast(fabs(h));   // |sqrt(der2) / h|
+        const double der12 = fmax(der2, detail::sqrt_fast(dnf));
+        const double h1 = (der12 <= 1.0e-15) ? fmax(1.0e-6, fabs(h) * 1.0e-3)
+                                             : detail::rcp_fast(detail::inv_eighth_root(0.01 * detail::rcp_fast(der12)));
+        h = fmin(100.0 * fabs(h), fmin(h1, hmax)) * posneg;
+    }
+#else
     {
         double dnf = 0.0, dny = 0.0;
 #pragma unroll
@@ -317,13 +328,76 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                                              : detail::pow_eighth(0.01 / der12);
         h = fmin(100.0 * fabs(h), fmin(h1, hmax)) * posneg;
     }
-    }  // if (alive)
+#endif
+    return h;
+}
+
+// Work feeder of the queue kernels (flowmap_kernel.cuh): lanes that have finished their particle
+// hand in the result and take the next pre-initialised one at the top of the attempt loop, so a
+// warp is not held by its slowest lane.  NoFeeder = one particle per lane, as everywhere else.
+struct NoFeeder {
+    static constexpr bool kActive = false;
+};
+
+// Integrates dy/ds = rhs(s, y) from s = x0 to s = xend.
+//   n_out  == 0 : only the final state is wanted (DENSE must be false)
+//   n_out  >= 2 : output times are t_k = p0 * (t0 + k*step), k = 0..n_out-1 (last = p0*(t0+T)),
+//                 rows 1..n_out-1 go to `sink`
+// Returns B200CS_ST_OK / _NMAX / _HSMALL; y holds the state reached.
+template <bool DENSE, bool LOCKSTEP, class Rhs, int N, class Sink, class KS, class Feeder = NoFeeder>
+__device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, double (&y)[N], double x0, double xend,
+                                                double rtol, double atol, int n_out, double out_p0,
+                                                double out_t0, double out_step, Sink &&sink,
+                                                StepCounts &cnt, KS K, Feeder &&feeder = Feeder{}) {
+    constexpr bool kFed = std::remove_reference_t<Feeder>::kActive;
+    static_assert(!(kFed && (DENSE || LOCKSTEP)), "the work feeder serves the final-time kernels");
+    constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
+    constexpr int kNmax = 100000;
+    constexpr int kSyncEvery = B200CS_SYNC_EVERY;
+    // K[1..12] stage slopes, K[13] FSAL slope, K[14..16] dense-output stages (registers or shared memory)
+    double aux[17];   // time-only part of the RHS per stage (flows that have one)
+    double x = x0;
+    const double posneg = (xend - x0) < 0.0 ? -1.0 : 1.0;
+    const double hmax = fabs(xend - x0);
+    bool last = false, reject = false;
+    int nstep = 0;
+    int iout = 1;  // next output row
+    // output time of row k, bit-identical to params[0]*np.linspace(t0, t0+T, n)[k]
+    auto t_out = [&](int k) { return __dmul_rn(out_p0, __dadd_rn(out_t0, __dmul_rn((double)k, out_step))); };
+    double tnext = 0.0;
+    if (DENSE) tnext = t_out(1);
+    // LOCKSTEP: every thread of the block calls this function (inactive ones idle) and the block
+    // meets at a barrier before each step attempt, so all its warps walk the large unrolled body
+    // together and share its instruction-cache footprint.
+    bool alive = active && !kFed;
+    double h = 0.0;
+    int status = active ? B200CS_ST_OK : B200CS_ST_MASKED;
+
+    if (alive && !kFed) h = dop853_start(rhs, x, y, rtol, atol, hmax, posneg, K);
 
     for (int it = 0;; ++it) {
         if (LOCKSTEP) {
             // re-align the block every kSyncEvery attempts (warps drift apart only slowly); the
             // loop is left at a barrier, by all threads together, once nobody is alive
             if ((it % kSyncEvery) == 0 && !__syncthreads_or(alive ? 1 : 0)) break;
+        } else if constexpr (kFed) {
+            if (__any_sync(0xffffffffu, !alive)) {
+                // all lanes call (the fetch is warp-cooperative); a lane that takes a particle comes back
+                // alive with y, h and the first slope of a fresh integration
+                if (feeder.refill(alive, y, h, K[1], status, cnt)) {
+                    x = x0;
+                    last = false;
+                    reject = false;
+                    nstep = 0;
+                    status = B200CS_ST_OK;
+                    cnt = StepCounts{};
+                    alive = true;
+                }
+                if (!__any_sync(0xffffffffu, alive)) {
+                    if (feeder.drained()) break;
+                    continue;
+                }
+            }
         } else if (!alive) {
             break;
         }
@@ -335,6 +409,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             last = true;
         }
         ++nstep;
+        const double xph = x + h;
         // the stage times x + c_s h are known now: the time-only part of the RHS is evaluated for
         // four stages at a time (four independent chains), off the stages' critical path
         detail::stage_aux<2, 4>(rhs, x, h, aux);
@@ -350,7 +425,6 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         detail::stage_aux<10, 3>(rhs, x, h, aux);  // c12 = 1: aux[12] also serves the FSAL slope
         detail::do_stage<10>(rhs, aux[10], x, h, y, K);
         detail::do_stage<11>(rhs, aux[11], x, h, y, K);
-        const double xph = x + h;
         {   // stage 12 is evaluated at x + h exactly
             double yy[N];
             detail::stage_arg<12, N>(yy, y, h, K, std::make_integer_sequence<int, 11>{});

@@ -33,6 +33,46 @@ struct KernelShape {
     static constexpr bool kLockstep = false;
     static constexpr bool kSlopesInSmem = false;
 };
+// Lane -> particle mapping of the final-time grid kernels.  kTileI == 1: a warp is 32 consecutive j
+// (one grid row segment).  kTileI == 4 / 8: a warp is a kTileI x (32 / kTileI) tile of the grid.  A
+// warp runs for as long as its slowest lane, and the attempt count of a particle is correlated
+// with its neighbours' in BOTH directions, so a compact tile wastes fewer lane-attempts than a
+// 32 x 1 strip (oracle attempt counts of config 2, bickley 2001 x 601, T = 6: lane efficiency 0.81
+// for 1 x 32, 0.87 for 4 x 8 / 8 x 4); the stores stay whole 128-byte lines for kTileI <= 4.
+// Measured (profiles/r3_ab_tile_hinit.txt; 1 x 32 -> 4 x 8 -> 8 x 4): double gyre 8192^2 1110.8 ->
+// 1126.8 -> 1124.2, Bickley config 2 250.1 -> 271.3 -> 275.4 (289.6 -> 306.3 -> 311.2 at 10.8 M
+// particles), spline probe 373.8 -> 389.2 -> 382.8 M points/s; outputs bit-identical.
+#ifndef B200CS_TILE_I
+#define B200CS_TILE_I 4
+#endif
+#ifndef B200CS_BICKLEY_TILE_I
+#define B200CS_BICKLEY_TILE_I 8
+#endif
+#ifndef B200CS_DG_TILE_I
+#define B200CS_DG_TILE_I B200CS_TILE_I
+#endif
+#ifndef B200CS_SPLINE_TILE_I
+#define B200CS_SPLINE_TILE_I B200CS_TILE_I
+#endif
+// kQueue (optional member of a KernelShape): the final-time grid / point-list launches of this flow
+// run as the QUEUE kernels below (lane-level work fetch) instead of one particle per thread.
+#ifndef B200CS_BICKLEY_QUEUE
+#define B200CS_BICKLEY_QUEUE 1
+#endif
+#ifndef B200CS_DG_QUEUE
+#define B200CS_DG_QUEUE 0
+#endif
+#ifndef B200CS_SPLINE_QUEUE
+#define B200CS_SPLINE_QUEUE 0
+#endif
+template <class T, class = void>
+struct shape_queue : std::false_type {};
+template <class T>
+struct shape_queue<T, std::void_t<decltype(T::kQueue)>> : std::bool_constant<T::kQueue> {};
+template <class T, class = void>
+struct shape_tile_i : std::integral_constant<int, B200CS_TILE_I> {};
+template <class T>
+struct shape_tile_i<T, std::void_t<decltype(T::kTileI)>> : std::integral_constant<int, T::kTileI> {};
 #ifndef B200CS_DG_THREADS
 #define B200CS_DG_THREADS 128
 #endif
@@ -48,6 +88,8 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
     static constexpr int kMinBlocks = B200CS_DG_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_DG_LOCKSTEP;
     static constexpr bool kSlopesInSmem = false;
+    static constexpr int kTileI = B200CS_DG_TILE_I;
+    static constexpr bool kQueue = B200CS_DG_QUEUE != 0;
 };
 // Bickley jet, final-time kernels: five blocks per SM (96 registers, 8 bytes of spills) measured
 // 207.9 against 204.1 M points/s uncapped (128 registers, four blocks) on config 2
@@ -80,6 +122,8 @@ struct KernelShape<BickleyJet, false> {
     static constexpr int kMinBlocks = B200CS_BICKLEY_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_BICKLEY_LOCKSTEP;
     static constexpr bool kSlopesInSmem = B200CS_BICKLEY_KSMEM;
+    static constexpr int kTileI = B200CS_BICKLEY_TILE_I;
+    static constexpr bool kQueue = B200CS_BICKLEY_QUEUE != 0;
 };
 // Round 2: with the 64-tap RHS out of line (B200CS_SPLINE_NOINLINE, flows.cuh) the attempt loop fits
 // the instruction cache, so the spline kernels run as free 128-thread blocks, five per SM (96
@@ -104,6 +148,8 @@ struct KernelShape<Spline2D<SPH, false>, false> {
     static constexpr int kMinBlocks = B200CS_SPLINE_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_SPLINE_LOCKSTEP;
     static constexpr bool kSlopesInSmem = B200CS_SPLINE_KSMEM;
+    static constexpr int kTileI = B200CS_SPLINE_TILE_I;
+    static constexpr bool kQueue = B200CS_SPLINE_QUEUE != 0;
 };
 
 template <int N>
@@ -132,13 +178,30 @@ struct RowSink {
 constexpr int kModePts = 0, kModeGrid = 1, kModeAux = 2, kModeSeries = 3;
 
 template <class Rhs, bool DENSE, int MODE>
+struct grid_tile_i {
+    static constexpr int value =
+        (MODE == kModeGrid && !DENSE && Rhs::N == 2) ? shape_tile_i<KernelShape<Rhs, DENSE>>::value : 1;
+};
+
+template <class Rhs, bool DENSE, int MODE>
 __global__ void __launch_bounds__(KernelShape<Rhs, DENSE>::kThreads, KernelShape<Rhs, DENSE>::kMinBlocks)
 flowmap_kernel(const __grid_constant__ IntegArgs A) {
     constexpr int N = Rhs::N;
     constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
     constexpr bool kLockstep = KernelShape<Rhs, DENSE>::kLockstep;
-    const long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
-    const bool in_range = q < A.npts;
+    constexpr int kTI = grid_tile_i<Rhs, DENSE, MODE>::value;
+    long long q = (long long)blockIdx.x * kBlock + threadIdx.x;
+    bool in_range = q < A.npts;
+    if constexpr (kTI > 1) {   // warp = kTI x (32 / kTI) tile of the grid (see shape_tile_i)
+        constexpr int kTJ = 32 / kTI;
+        const long long w = q >> 5;
+        const int lane = threadIdx.x & 31;
+        const long long tiles_j = (A.ny + kTJ - 1) / kTJ;
+        const long long ti = w / tiles_j, tj = w - ti * tiles_j;
+        const long long i = ti * kTI + lane / kTJ, j = tj * kTJ + lane % kTJ;
+        in_range = i < A.nx && j < A.ny;
+        q = in_range ? i * A.ny + j : 0;
+    }
     bool active = in_range;
     if (MODE != kModeAux && MODE != kModeSeries && active && A.mask != nullptr) active = (A.mask[q] == 0);
     double x0 = A.x0, xend = A.xend;   // warp-uniform except in kModeSeries
@@ -354,11 +417,214 @@ inline int rhs_slot_for_stream(cudaStream_t s) {
     return (int)seen.size() - 1;
 }
 
+// ---- queue kernels: lane-level work fetch for flows whose particles need very different numbers
+// of step attempts ---------------------------------------------------------------------------
+// With one particle per thread a warp runs for as long as its slowest lane: on config 2 (Bickley jet
+// 2001 x 601, T = 6; 6..61 attempts per particle) the oracle's attempt counts give a lane
+// efficiency of 0.81 for 32 x 1 strips and 0.87 for 8 x 4 tiles, and ncu counts 25.2 of 32 lanes
+// active.  Here the integration is split in two launches:
+//   flowmap_init_kernel   one thread per particle SLOT (tile order): initial condition, mask, first
+//                         slope and hinit -- warp-uniform code, nothing diverges -- parked as 48
+//                         bytes of state per slot (SoA: y, first slope, h, output index; index -1
+//                         marks a slot without work, whose zeros / MASKED status this kernel has
+//                         already written);
+//   flowmap_queue_kernel  a persistent grid; every lane that finishes its particle stores the result
+//                         and takes the next slot from a global counter (one warp-aggregated
+//                         atomicAdd per refill) at the top of the attempt loop, so only the tail of the
+//                         whole launch idles lanes.
+// Every particle is integrated by exactly the same instruction sequence as in flowmap_kernel: the
+// results are bit-identical (tools/grid_hash.py, tests/test_gpu_parity.py::test_queue_kernel_*).
+template <int TI, int MODE>
+__device__ __forceinline__ long long slot_to_particle(long long qi, const IntegArgs &A) {
+    if (MODE == kModeGrid) {
+        constexpr int kTJ = 32 / TI;
+        const long long w = qi >> 5;
+        const int lane = (int)(qi & 31);
+        const long long tiles_j = (A.ny + kTJ - 1) / kTJ;
+        const long long ti = w / tiles_j, tj = w - ti * tiles_j;
+        const long long i = ti * TI + lane / kTJ, j = tj * kTJ + lane % kTJ;
+        return (i < A.nx && j < A.ny) ? i * A.ny + j : -1;
+    }
+    return qi < A.npts ? qi : -1;
+}
+
+template <class Rhs, int MODE>
+struct queue_tile_i {
+    static constexpr int raw = shape_tile_i<KernelShape<Rhs, false>>::value;
+    static constexpr int value = (MODE == kModeGrid) ? (raw > 1 ? raw : 1) : 1;
+};
+
+template <class Rhs, int MODE>
+__global__ void __launch_bounds__(128) flowmap_init_kernel(const __grid_constant__ IntegArgs A) {
+    static_assert(Rhs::N == 2, "queue kernels: 2-D flows");
+    constexpr int kTI = queue_tile_i<Rhs, MODE>::value;
+    const long long qi = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (qi >= A.nq) return;
+    const long long q = slot_to_particle<kTI, MODE>(qi, A);
+    bool active = q >= 0;
+    if (active && A.mask != nullptr) active = (A.mask[q] == 0);
+    double y[2] = {0.0, 0.0}, k1[2] = {0.0, 0.0}, h = 0.0;
+    if (active) {
+        if (MODE == kModeGrid) {
+            const long long i = q / A.ny, j = q - i * A.ny;
+            y[0] = A.x[i];
+            y[1] = A.y[j];
+        } else {
+            y[0] = A.pts[2 * q];
+            y[1] = A.pts[2 * q + 1];
+        }
+        const Rhs rhs(A.rhs);
+        RegSlopes<2> K;
+        const double posneg = (A.xend - A.x0) < 0.0 ? -1.0 : 1.0;
+        h = dop853_start(rhs, A.x0, y, A.rtol, A.atol, fabs(A.xend - A.x0), posneg, K);
+        k1[0] = K[1][0];
+        k1[1] = K[1][1];
+    } else if (q >= 0) {   // masked: zeros (integration.py:163), final here
+        if (A.out_aligned16) *reinterpret_cast<double2 *>(A.out + 2 * q) = make_double2(0.0, 0.0);
+        else A.out[2 * q] = A.out[2 * q + 1] = 0.0;
+        if (A.status) A.status[q] = B200CS_ST_MASKED;
+        if (A.steps) A.steps[2 * q] = A.steps[2 * q + 1] = 0;
+    }
+    A.qstate[qi] = y[0];
+    A.qstate[A.nq + qi] = y[1];
+    A.qstate[2 * A.nq + qi] = k1[0];
+    A.qstate[3 * A.nq + qi] = k1[1];
+    A.qstate[4 * A.nq + qi] = h;
+    // slot -> particle (output index), -1 for a slot without work: the refill needs no index arithmetic
+    reinterpret_cast<long long *>(A.qstate)[5 * A.nq + qi] = active ? q : -1;
+}
+
+template <int TI, int MODE>
+struct QueueFeeder {
+    static constexpr bool kActive = true;
+    const IntegArgs &A;
+    long long q = -1;     // particle in flight (output index), -1: none
+    bool done = false;    // the counter has passed the last slot (warp-uniform)
+    unsigned long long nfev = 0, acc = 0, rej = 0;
+    __device__ __forceinline__ explicit QueueFeeder(const IntegArgs &A_) : A(A_) {}
+    __device__ __forceinline__ bool drained() const { return done; }
+    // Called by ALL lanes of the warp.  A lane that is not alive first hands in the particle it holds
+    // (final state, status, step counts), then takes the next slot with work, if any: returns true
+    // with y, h and the first slope k1 of the new particle.
+    __device__ __forceinline__ bool refill(bool alive, double (&y)[2], double &h, double (&k1)[2], int status,
+                                           const StepCounts &cnt) {
+        if (!alive && q >= 0) {
+            if (A.out_aligned16) *reinterpret_cast<double2 *>(A.out + 2 * q) = make_double2(y[0], y[1]);
+            else { A.out[2 * q] = y[0]; A.out[2 * q + 1] = y[1]; }
+            if (A.status) A.status[q] = status;
+            if (A.steps) {
+                A.steps[2 * q] = cnt.accepted;
+                A.steps[2 * q + 1] = cnt.rejected;
+            }
+            nfev += 2ull + 11ull * (unsigned)(cnt.accepted + cnt.rejected) + (unsigned)cnt.accepted;
+            acc += (unsigned)cnt.accepted;
+            rej += (unsigned)cnt.rejected;
+            q = -1;
+        }
+        if (done) return false;
+        const unsigned lane = threadIdx.x & 31;
+        const unsigned idle = __ballot_sync(0xffffffffu, !alive);
+        const int n = __popc(idle);
+        const int leader = __ffs(idle) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(A.qcounter, (unsigned long long)n);
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if ((long long)(base + n) >= A.nq) done = true;
+        if (alive) return false;
+        const long long qi = (long long)base + __popc(idle & ((1u << lane) - 1u));
+        if (qi >= A.nq) return false;
+        const long long qn = reinterpret_cast<const long long *>(A.qstate)[5 * A.nq + qi];
+        if (qn < 0) return false;   // masked, or an empty slot of an edge tile
+        y[0] = A.qstate[qi];
+        y[1] = A.qstate[A.nq + qi];
+        k1[0] = A.qstate[2 * A.nq + qi];
+        k1[1] = A.qstate[3 * A.nq + qi];
+        h = A.qstate[4 * A.nq + qi];
+        q = qn;
+        return true;
+    }
+};
+
+template <class Rhs, int MODE>
+__global__ void __launch_bounds__(KernelShape<Rhs, false>::kThreads, KernelShape<Rhs, false>::kMinBlocks)
+flowmap_queue_kernel(const __grid_constant__ IntegArgs A) {
+    constexpr int kTI = queue_tile_i<Rhs, MODE>::value;
+    const Rhs rhs(A.rhs);
+    QueueFeeder<kTI, MODE> feeder(A);
+    double y[2] = {0.0, 0.0};
+    StepCounts cnt;
+    dop853_integrate<false, false>(rhs, true, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0, 0.0, NoSink<2>{}, cnt,
+                                   RegSlopes<2>{}, feeder);
+    if (A.stats) {
+        unsigned long long nfev = feeder.nfev, acc = feeder.acc, rej = feeder.rej;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nfev += __shfl_down_sync(0xffffffffu, nfev, o);
+            acc += __shfl_down_sync(0xffffffffu, acc, o);
+            rej += __shfl_down_sync(0xffffffffu, rej, o);
+        }
+        if ((threadIdx.x & 31) == 0 && nfev) {
+            atomicAdd(&A.stats[0], nfev);
+            atomicAdd(&A.stats[1], acc);
+            atomicAdd(&A.stats[2], rej);
+        }
+    }
+}
+
+// smallest launch that goes through the queue kernels (below it one wave of flowmap_kernel is as good)
+constexpr long long kQueueMinParticles = 1 << 16;
+
+template <class Rhs, int MODE>
+void launch_queue(const IntegArgs &A0, cudaStream_t s) {
+    constexpr int kTI = queue_tile_i<Rhs, MODE>::value;
+    constexpr int kBlock = KernelShape<Rhs, false>::kThreads;
+    IntegArgs A = A0;
+    A.nq = A.npts;
+    if (MODE == kModeGrid) A.nq = ((A.nx + kTI - 1) / kTI) * ((A.ny + 32 / kTI - 1) / (32 / kTI)) * 32;
+    Scratch st((size_t)A.nq * 6 * sizeof(double) + 64, s);
+    A.qstate = static_cast<double *>(st.ptr);
+    A.qcounter = reinterpret_cast<unsigned long long *>(A.qstate + 6 * A.nq);
+    B2_CHECK_CUDA(cudaMemsetAsync(A.qcounter, 0, sizeof(unsigned long long), s));
+    const long long init_blocks = (A.nq + 127) / 128;
+    B2_REQUIRE(init_blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
+    static int resident = 0;   // blocks of the queue kernel the device holds at once
+    if (resident == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        B2_CHECK_CUDA(cudaGetDevice(&dev));
+        B2_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        B2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flowmap_queue_kernel<Rhs, MODE>, kBlock, 0));
+        resident = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const long long want = (A.nq + kBlock - 1) / kBlock;
+    const unsigned blocks = (unsigned)(want < resident ? want : resident);
+#if B200CS_RHS_SLOTS
+    if constexpr (rhs_out_of_line<Rhs>::value) {
+        A.rhs.slot = rhs_slot_for_stream(s);
+        B2_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_rhs_slots, &A.rhs, sizeof(RhsParams), sizeof(RhsParams) * A.rhs.slot,
+                                              cudaMemcpyHostToDevice, s));
+    }
+#endif
+    flowmap_init_kernel<Rhs, MODE><<<(unsigned)init_blocks, 128, 0, s>>>(A);
+    B2_CHECK_CUDA(cudaGetLastError());
+    flowmap_queue_kernel<Rhs, MODE><<<blocks, kBlock, 0, s>>>(A);
+    B2_CHECK_CUDA(cudaGetLastError());
+}
+
 template <class Rhs, bool DENSE, int MODE>
 void launch_one(const IntegArgs &A, cudaStream_t s) {
     constexpr int kBlock = KernelShape<Rhs, DENSE>::kThreads;
-    const long long blocks = (A.npts + kBlock - 1) / kBlock;
+    constexpr int kTI = grid_tile_i<Rhs, DENSE, MODE>::value;
+    long long threads = A.npts;
+    if constexpr (kTI > 1) threads = ((A.nx + kTI - 1) / kTI) * ((A.ny + 32 / kTI - 1) / (32 / kTI)) * 32;
+    const long long blocks = A.npts > 0 ? (threads + kBlock - 1) / kBlock : 0;
     if (blocks <= 0) return;
+    if constexpr (shape_queue<KernelShape<Rhs, DENSE>>::value && !DENSE && Rhs::N == 2 &&
+                  (MODE == kModeGrid || MODE == kModePts)) {
+        if (A.npts >= kQueueMinParticles && A.xend != A.x0 && A.out != nullptr) {
+            launch_queue<Rhs, MODE>(A, s);
+            return;
+        }
+    }
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
 #if B200CS_RHS_SLOTS
     if constexpr (rhs_out_of_line<Rhs>::value) {   // the flows with an out-of-line RHS (spline / linear)

@@ -39,6 +39,11 @@ struct IntegArgs {
     const double *vort_avg;    // [n_out] spatial means
     double period_x, period_y;
     double *lavd;              // [npts]
+    // queue kernels (flowmap_kernel.cuh): nq pre-initialised particle slots, SoA qstate[6][nq] =
+    // (y0, y1, k1_0, k1_1, h, output index as int64: -1 for a slot without work), the fetch counter
+    double *qstate;
+    unsigned long long *qcounter;
+    long long nq;
 };
 
 void launch_flowmap(const FlowSpec &f, const IntegArgs &A, int mode /*0 pts, 1 grid, 2 aux grid, 3 time series*/,
