@@ -70,6 +70,18 @@
 #ifndef B200CS_CTRL_FAST
 #define B200CS_CTRL_FAST (!B200CS_STRICT_INT)
 #endif
+// B200CS_CTRL_ONE_NEWTON (round 2, last session): one Newton step instead of two for 1/sk and
+// err^(-1/8) (rcp_fast1 / inv_eighth_root1 below say why that cannot reach the parity figures):
+// 804 -> 794 FP64 instructions per double-gyre attempt, 1132.9 -> 1148.8 M points/s at 8192^2,
+// config-1 parity figures identical to the last digit (profiles/r3_ab_lockstep_queue.txt).
+#ifndef B200CS_CTRL_ONE_NEWTON
+#define B200CS_CTRL_ONE_NEWTON B200CS_CTRL_FAST
+#endif
+// lockstep QUEUE kernels re-align more often than the plain lockstep kernels: their warps never run
+// dry, so a barrier costs only the skew of one or two attempts
+#ifndef B200CS_QSYNC_EVERY
+#define B200CS_QSYNC_EVERY 3   // every 2 / 3 / 4 attempts: 321.6 / 325.4 / 325.7 (config 2), 362.8 / 366.9 / 359.5 M points/s (10.8 M particles)
+#endif
 #ifndef B200CS_FSAL_ALWAYS
 #define B200CS_FSAL_ALWAYS 0
 #endif
@@ -191,6 +203,25 @@ __device__ __forceinline__ double inv_eighth_root(double x) {
     return z;
 }
 #endif
+// The one-Newton-step forms (B200CS_CTRL_ONE_NEWTON): 1/sk to ~6e-14 and err^(-1/8) to ~5e-12 relative.
+// The scaled error of a step moves by 6e-14 relative (an accept / reject test err <= 1 flips for
+// ~1e-4 particles of a 2.7e8-particle grid), the next step size by 5e-12 relative, which moves a
+// step's result by 8 x (local error ~1e-6) x 5e-12 = 4e-17: far below the 1-ulp noise of the RHS.
+__device__ __forceinline__ double rcp_fast1(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return fma(r, fma(-x, r, 1.0), r);
+}
+__device__ __forceinline__ double inv_eighth_root1(double x) {
+    double s1, s2, z;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s1) : "d"(x));
+    const double t1 = x * s1;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(s2) : "d"(t1));
+    const double t2 = t1 * s2;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(z) : "d"(t2));
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    return fma(z * fma(-x, z8, 1.0), 0.125, z);
+}
 // a / c for a compile-time constant c: q = a*rc, one FMA residual correction -> the correctly
 // rounded quotient in 3 FP64 instructions (see tensor_kernels.cu, div_const)
 __device__ __forceinline__ double div_const(double a, double c, double rc) {
@@ -350,7 +381,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                                                 double out_t0, double out_step, Sink &&sink,
                                                 StepCounts &cnt, KS K, Feeder &&feeder = Feeder{}) {
     constexpr bool kFed = std::remove_reference_t<Feeder>::kActive;
-    static_assert(!(kFed && (DENSE || LOCKSTEP)), "the work feeder serves the final-time kernels");
+    static_assert(!(kFed && DENSE), "the work feeder serves the final-time kernels");
     constexpr double kSafe = 0.9, kFacc1 = 1.0 / 0.333, kFacc2 = 1.0 / 6.0, kURound = 2.3e-16;
     constexpr int kNmax = 100000;
     constexpr int kSyncEvery = B200CS_SYNC_EVERY;
@@ -376,11 +407,26 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
     if (alive && !kFed) h = dop853_start(rhs, x, y, rtol, atol, hmax, posneg, K);
 
     for (int it = 0;; ++it) {
-        if (LOCKSTEP) {
+        if constexpr (kFed && LOCKSTEP) {
+            // queue kernel in lockstep: warps refill on their own, the block re-aligns every kSyncEvery
+            // attempts and leaves together once no lane is alive and every warp has seen the queue empty
+            if (__any_sync(0xffffffffu, !alive)) {
+                if (feeder.refill(alive, y, h, K[1], status, cnt)) {
+                    x = x0;
+                    last = false;
+                    reject = false;
+                    nstep = 0;
+                    status = B200CS_ST_OK;
+                    cnt = StepCounts{};
+                    alive = true;
+                }
+            }
+            if ((it % B200CS_QSYNC_EVERY) == 0 && !__syncthreads_or((alive || !feeder.drained()) ? 1 : 0)) break;
+        } else if (LOCKSTEP) {
             // re-align the block every kSyncEvery attempts (warps drift apart only slowly); the
             // loop is left at a barrier, by all threads together, once nobody is alive
             if ((it % kSyncEvery) == 0 && !__syncthreads_or(alive ? 1 : 0)) break;
-        } else if constexpr (kFed) {
+        } else if constexpr (kFed && !LOCKSTEP) {
             if (__any_sync(0xffffffffu, !alive)) {
                 // all lanes call (the fetch is warp-cooperative); a lane that takes a particle comes back
                 // alive with y, h and the first slope of a fresh integration
@@ -449,7 +495,11 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             e3 = detail::mad(-dop::kTab.bhh[1], K[9][i], e3);
             e3 = detail::mad(-dop::kTab.bhh[2], K[12][i], e3);
 #if B200CS_CTRL_FAST
+#if B200CS_CTRL_ONE_NEWTON
+            const double rsk = detail::rcp_fast1(sk);
+#else
             const double rsk = detail::rcp_fast(sk);  // sk = atol + rtol |y| is a normal positive number
+#endif
             e3 *= rsk;
 #elif B200CS_LEAN
             const double rsk = 1.0 / sk;  // one reciprocal serves both estimates (<= 1 ulp from e/sk)
@@ -483,7 +533,11 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
 #if B200CS_CTRL_FAST
         // g = 0.9 err^(-1/8) = 1 / (fac11 / safe); err == 0 (or below the seed's range) -> +inf, i.e. the
         // growth clamp; a NaN err stays NaN and fmax / fmin then pick the 1/3 of a rejected step
+#if B200CS_CTRL_ONE_NEWTON
+        double g = kSafe * detail::inv_eighth_root1(err);
+#else
         double g = kSafe * detail::inv_eighth_root(err);
+#endif
         if (err <= 1.0e-280) g = __longlong_as_double(0x7ff0000000000000LL);
         double hnew = h * fmin(1.0 / kFacc2, fmax(1.0 / kFacc1, g));
 #else

@@ -65,8 +65,37 @@ struct KernelShape {
 #ifndef B200CS_SPLINE_QUEUE
 #define B200CS_SPLINE_QUEUE 0
 #endif
+// Launch shape of the Bickley queue kernel: ONE 640-thread lockstep block per SM (96 registers).  The
+// unrolled attempt of this flow is 49 KB of code against a 32 KB instruction cache (ncu on the free
+// 128-thread shape: no_instruction 2.2 cycles per issue, the largest stall after the fixed-latency
+// wait); in lockstep the 20 warps of an SM stream through it together.  What made lockstep lose in
+// round 2 -- warps that ran out of particles idling at the barrier until the block's slowest lane
+// was done -- is gone with the queue: every warp refills until the whole launch is drained.
+// Measured on config 2 / at 10.8 M particles (profiles/r3_ab_lockstep_queue.txt): free 128 x 5
+// 288.9 / 319.1, lockstep 640 x 1 re-aligned every 8 / 2 / 1 attempts 317.9 / 319.8 / 314.9 and
+// 351.1 / 360.6 / 354.1, 512 x 1 (128 registers) 318.3 / 338.6, 320 x 2 287.6 / 321.5 M points/s.
+#ifndef B200CS_BICKLEY_QTHREADS
+#define B200CS_BICKLEY_QTHREADS 640
+#endif
+#ifndef B200CS_BICKLEY_QMINBLOCKS
+#define B200CS_BICKLEY_QMINBLOCKS 1
+#endif
+#ifndef B200CS_BICKLEY_QLOCKSTEP
+#define B200CS_BICKLEY_QLOCKSTEP true
+#endif
 template <class T, class = void>
 struct shape_queue : std::false_type {};
+// launch shape of the queue kernel: kQThreads / kQMinBlocks / kQLockstep of the KernelShape, else its plain shape
+template <class T, class = void>
+struct queue_shape {
+    static constexpr int kThreads = T::kThreads, kMinBlocks = T::kMinBlocks;
+    static constexpr bool kLockstep = false;
+};
+template <class T>
+struct queue_shape<T, std::void_t<decltype(T::kQThreads)>> {
+    static constexpr int kThreads = T::kQThreads, kMinBlocks = T::kQMinBlocks;
+    static constexpr bool kLockstep = T::kQLockstep;
+};
 template <class T>
 struct shape_queue<T, std::void_t<decltype(T::kQueue)>> : std::bool_constant<T::kQueue> {};
 template <class T, class = void>
@@ -124,6 +153,8 @@ struct KernelShape<BickleyJet, false> {
     static constexpr bool kSlopesInSmem = B200CS_BICKLEY_KSMEM;
     static constexpr int kTileI = B200CS_BICKLEY_TILE_I;
     static constexpr bool kQueue = B200CS_BICKLEY_QUEUE != 0;
+    static constexpr int kQThreads = B200CS_BICKLEY_QTHREADS, kQMinBlocks = B200CS_BICKLEY_QMINBLOCKS;
+    static constexpr bool kQLockstep = B200CS_BICKLEY_QLOCKSTEP;
 };
 // Round 2: with the 64-tap RHS out of line (B200CS_SPLINE_NOINLINE, flows.cuh) the attempt loop fits
 // the instruction cache, so the spline kernels run as free 128-thread blocks, five per SM (96
@@ -348,10 +379,26 @@ struct LavdSink {
     }
 };
 
+// The fused LAVD kernel keeps 32 x 1 strips: its cost is the 64-tap VORTICITY gather at 601 output
+// times per particle, whose lanes coalesce along y (config 4: 32.2 ms with strips, 36.4 ms with 4 x 8
+// tiles, profiles/r3_configs_c1_c4.json / r3_configs_c1_c4_lavd_tile4.json).
+#ifndef B200CS_LAVD_TILE_I
+#define B200CS_LAVD_TILE_I 1
+#endif
 template <class Rhs>
 __global__ void __launch_bounds__(128) lavd_flowmap_kernel(const __grid_constant__ IntegArgs A) {
     static_assert(Rhs::N == 2, "LAVD is defined for 2-D flows");
-    const long long q = (long long)blockIdx.x * 128 + threadIdx.x;
+    constexpr int kTI = B200CS_LAVD_TILE_I, kTJ = 32 / kTI;   // warp = kTI x kTJ tile of the grid (shape_tile_i)
+    long long q = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (kTI > 1) {
+        const long long w = q >> 5;
+        const int lane = threadIdx.x & 31;
+        const long long tiles_j = (A.ny + kTJ - 1) / kTJ;
+        const long long ti = w / tiles_j, tj = w - ti * tiles_j;
+        const long long i = ti * kTI + lane / kTJ, j = tj * kTJ + lane % kTJ;
+        if (i >= A.nx || j >= A.ny) return;
+        q = i * A.ny + j;
+    }
     if (q >= A.npts) return;
     const bool active = (A.mask == nullptr || A.mask[q] == 0);
     double y[2] = {0.0, 0.0};
@@ -392,7 +439,10 @@ __global__ void __launch_bounds__(128) lavd_flowmap_kernel(const __grid_constant
 
 template <class Rhs>
 void launch_lavd_one(const IntegArgs &A, cudaStream_t s) {
-    const long long blocks = (A.npts + 127) / 128;
+    constexpr int kTI = B200CS_LAVD_TILE_I;
+    long long threads = A.npts;
+    if (kTI > 1) threads = ((A.nx + kTI - 1) / kTI) * ((A.ny + 32 / kTI - 1) / (32 / kTI)) * 32;
+    const long long blocks = A.npts > 0 ? (threads + 127) / 128 : 0;
     if (blocks <= 0) return;
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
     lavd_flowmap_kernel<Rhs><<<(unsigned)blocks, 128, 0, s>>>(A);
@@ -546,15 +596,17 @@ struct QueueFeeder {
 };
 
 template <class Rhs, int MODE>
-__global__ void __launch_bounds__(KernelShape<Rhs, false>::kThreads, KernelShape<Rhs, false>::kMinBlocks)
+__global__ void __launch_bounds__(queue_shape<KernelShape<Rhs, false>>::kThreads,
+                                  queue_shape<KernelShape<Rhs, false>>::kMinBlocks)
 flowmap_queue_kernel(const __grid_constant__ IntegArgs A) {
     constexpr int kTI = queue_tile_i<Rhs, MODE>::value;
+    constexpr bool kLockstep = queue_shape<KernelShape<Rhs, false>>::kLockstep;
     const Rhs rhs(A.rhs);
     QueueFeeder<kTI, MODE> feeder(A);
     double y[2] = {0.0, 0.0};
     StepCounts cnt;
-    dop853_integrate<false, false>(rhs, true, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0, 0.0, NoSink<2>{}, cnt,
-                                   RegSlopes<2>{}, feeder);
+    dop853_integrate<false, kLockstep>(rhs, true, y, A.x0, A.xend, A.rtol, A.atol, 0, 0.0, 0.0, 0.0, NoSink<2>{}, cnt,
+                                       RegSlopes<2>{}, feeder);
     if (A.stats) {
         unsigned long long nfev = feeder.nfev, acc = feeder.acc, rej = feeder.rej;
 #pragma unroll
@@ -577,7 +629,7 @@ constexpr long long kQueueMinParticles = 1 << 16;
 template <class Rhs, int MODE>
 void launch_queue(const IntegArgs &A0, cudaStream_t s) {
     constexpr int kTI = queue_tile_i<Rhs, MODE>::value;
-    constexpr int kBlock = KernelShape<Rhs, false>::kThreads;
+    constexpr int kBlock = queue_shape<KernelShape<Rhs, false>>::kThreads;
     IntegArgs A = A0;
     A.nq = A.npts;
     if (MODE == kModeGrid) A.nq = ((A.nx + kTI - 1) / kTI) * ((A.ny + 32 / kTI - 1) / (32 / kTI)) * 32;
