@@ -28,7 +28,12 @@
 // parity select, constants folded on the host, damping compiled out): it fits the I-cache, so the
 // double-gyre kernels run as free 128-thread blocks, five per SM (no barrier, no block tail where
 // 8 % of the warp-time idled), FP64 pipe 59 % -> 82 % busy, 664 -> 1014 M points/s at 16384^2.
-// The spline kernels, whose 64-tap RHS makes the loop far larger, keep the lockstep shape.
+// Round 2: the spline kernels run free too (their 64-tap RHS went out of line); a warp of the
+// final-time grid kernels is a 4 x 8 tile of the particle grid, not a 32 x 1 strip (fewer idle
+// lane-attempts); and the Bickley jet, whose unrolled attempt is 49 KB, runs as a LOCKSTEP QUEUE
+// kernel: one 640-thread block per SM whose lanes fetch the next pre-initialised particle when
+// they finish (the Feeder hook below) -- lockstep shares the instruction-cache footprint, the
+// queue removes what lockstep used to cost (flowmap_kernel.cuh).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -132,10 +137,21 @@ struct SmemSlopes {
     static constexpr bool kDirect = false;
     double *base;   // shared memory, already offset by the thread index
     int stride;     // threads per block
+    // reads are volatile: without that ptxas forwards every stored slope in registers (the addresses are
+    // provably thread-private) and the point of parking them -- fewer live registers -- is lost
+    struct Ref {
+        double *q;
+        __device__ __forceinline__ operator double() const { return *reinterpret_cast<volatile double *>(q); }
+        __device__ __forceinline__ Ref &operator=(double v) {
+            *q = v;
+            return *this;
+        }
+        __device__ __forceinline__ Ref &operator=(const Ref &o) { return *this = (double)o; }
+    };
     struct Row {
         double *p;
         int stride;
-        __device__ __forceinline__ double &operator[](int i) const { return p[i * stride]; }
+        __device__ __forceinline__ Ref operator[](int i) const { return Ref{p + i * stride}; }
     };
     __device__ __forceinline__ Row operator[](int s) const { return Row{base + s * N * stride, stride}; }
 };

@@ -108,6 +108,9 @@ struct shape_tile_i<T, std::void_t<decltype(T::kTileI)>> : std::integral_constan
 #ifndef B200CS_DG_LOCKSTEP
 #define B200CS_DG_LOCKSTEP false
 #endif
+#ifndef B200CS_DG_KSMEM   // A/B: stage slopes in shared memory to run 6 / 7 blocks per SM (80 / 72 registers):
+#define B200CS_DG_KSMEM false   // 1044 / 1046 against 1150 M points/s at 8192^2 (profiles/r3_ab_dg_ksmem.txt)
+#endif
 #ifndef B200CS_DG_MINBLOCKS
 #define B200CS_DG_MINBLOCKS 5
 #endif
@@ -116,7 +119,7 @@ struct KernelShape<DoubleGyreT<DAMPED>, false> {
     static constexpr int kThreads = B200CS_DG_THREADS;
     static constexpr int kMinBlocks = B200CS_DG_MINBLOCKS;
     static constexpr bool kLockstep = B200CS_DG_LOCKSTEP;
-    static constexpr bool kSlopesInSmem = false;
+    static constexpr bool kSlopesInSmem = B200CS_DG_KSMEM;
     static constexpr int kTileI = B200CS_DG_TILE_I;
     static constexpr bool kQueue = B200CS_DG_QUEUE != 0;
 };

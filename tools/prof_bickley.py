@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Profiling driver for the Bickley-jet flow-map kernel (BASELINE config 2: 2001 x 601, T = +6),
 device-resident.  Under ncu:
-    ncu --set full --clock-control none --import-source on -k regex:flowmap_kernel -s 1 -c 1 \
+    ncu --set full --clock-control none --import-source on -k regex:flowmap_queue_kernel -s 1 -c 1 \
         -o gpurun_out/bickley python tools/prof_bickley.py [scale=1] [reps=2]
 `scale` multiplies both grid dimensions (scale=3 fills the machine: 10.8 M particles)."""
 import os

@@ -32,4 +32,4 @@ loop = [(a, op) for a, op, _ in ins if lo <= a <= hi]
 c = Counter(op.split(".")[0] for _, op in loop)
 fp64 = sum(c[k] for k in ("DFMA", "DMUL", "DADD", "DSETP"))
 print(f"{fn[-60:]}: {len(ins)} instructions, loop 0x{lo:x}-0x{hi:x} = {len(loop)}")
-print(f"  FP64 {fp64}  other {len(loop) - fp64}  | " + "  ".join(f"{k} {v}" for k, v in c.most_common(14)))
+print(f"  FP64 {fp64}  other {len(loop) - fp64}  | " + "  ".join(f"{k} {v}" for k, v in c.most_common(24)))
