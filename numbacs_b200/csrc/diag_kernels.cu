@@ -6,6 +6,8 @@
 //       Simpson rule as in utils.py:611-655 (even number of intervals: 1/3 rule; odd: 1/3 rule on
 //       the first n-1 intervals plus the three-point end correction).
 // The prefilter replaces interpolation.splines.prefilter(grid, data, k=3) (flows.py:43-44, 116).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "launch.cuh"
 #include "spline.cuh"
@@ -87,6 +89,92 @@ __global__ void curl_tspan_kernel(const SplineGridDev g, const double2 *__restri
 
 constexpr int kRedThreads = 256;
 
+// W[k, m, n] = the field contracted over time at t = tspan[k] (spline.cuh: eval_spline_s2 / eval_linear_s2):
+// cubic  sum_a P0[a] C[i0 + a, m, n]  in the order of eval_spline_s's outer sum; trilinear
+// (1 - l0) F[i0] + l0 F[i0 + 1].  A time outside the grid in 'constant' mode gives a zero slab.
+__global__ void __launch_bounds__(256)
+vort_slab_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ tspan, long long slab,
+                 double *__restrict__ W) {
+    const long long k = blockIdx.y;
+    double t = tspan[k];
+    double *Wk = W + k * slab;
+    const bool inside = extrap_coord(S.g, 0, t);
+    int i0 = 0;
+    double l0 = 0.0;
+    if (inside) axis_locate(S.g, 0, t, i0, l0);
+    double P0[4] = {0.0, 0.0, 0.0, 0.0};
+    if (inside && !S.linear) bspline_weights(l0, S.g.extrap == B200CS_EXTRAP_LINEAR, P0);
+    const double *c = S.C + (long long)i0 * S.g.s0;
+    for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < slab; e += (long long)gridDim.x * 256) {
+        double v = 0.0;
+        if (inside) {
+            if (S.linear) {
+                v = sp_mad(l0, __ldg(c + S.g.s0 + e), (1.0 - l0) * __ldg(c + e));
+            } else {
+#pragma unroll
+                for (int a = 0; a < 4; ++a) v = sp_mad(P0[a], __ldg(c + a * S.g.s0 + e), v);
+            }
+        }
+        Wk[e] = v;
+    }
+}
+
+// Spatial sums over an 'ij' grid of particles without touching a particle: the evaluator is a tensor
+// product, so  sum_ij f(x_i, y_j) = sum_m sum_n WX[m] W[m, n] WY[n]  with the blending weights of
+// all x_i (y_j) accumulated per coefficient row (column).  aw[m] = sum_i weight of point i on row m
+// of axis d, in ascending i (deterministic); the extrapolation rule of the axis is applied per point.
+__global__ void axis_weights_kernel(const __grid_constant__ ScalarDev S, int d, const double *__restrict__ pts,
+                                    long long npts, int rows, double *__restrict__ aw) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    const bool lin = S.g.extrap == B200CS_EXTRAP_LINEAR;
+    double acc = 0.0;
+    for (long long i = 0; i < npts; ++i) {
+        double x = __ldg(pts + i);
+        if (!extrap_coord(S.g, d, x)) continue;
+        int i1;
+        double l;
+        axis_locate(S.g, d, x, i1, l);
+        const int o = m - i1;
+        if (S.linear) {
+            if (o == 0) acc += 1.0 - l;
+            else if (o == 1) acc += l;
+        } else if (o >= 0 && o < 4) {
+            double P[4];
+            bspline_weights(l, lin, P);
+            acc += (o == 0) ? P[0] : (o == 1) ? P[1] : (o == 2) ? P[2] : P[3];
+        }
+    }
+    aw[m] = acc;
+}
+
+// sums[k] = sum_m WX[m] sum_n W[k, m, n] WY[n]: one block per output time, one warp per row, fixed order
+__global__ void __launch_bounds__(256)
+slab_bilinear_kernel(const double *__restrict__ W, long long slab, int rows, int cols, long long s1,
+                     const double *__restrict__ wx, const double *__restrict__ wy, double *__restrict__ sums) {
+    __shared__ double red[8];
+    const double *Wk = W + (long long)blockIdx.x * slab;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc = 0.0;
+    for (int m = warp; m < rows; m += 8) {
+        const double a = __ldg(wx + m);
+        if (a == 0.0) continue;   // rows no particle touches (warp-uniform)
+        const double *row = Wk + (long long)m * s1;
+        double p = 0.0;
+        for (int n = lane; n < cols; n += 32) p = fma(__ldg(row + n), __ldg(wy + n), p);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+        acc = fma(a, p, acc);
+    }
+    if (lane == 0) red[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        sums[blockIdx.x] = t;
+    }
+}
+
 // partial[k * gridDim.x + b] = sum over the block's strided share of the points
 __global__ void __launch_bounds__(kRedThreads)
 vort_partial_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__ tspan,
@@ -99,7 +187,7 @@ vort_partial_kernel(const __grid_constant__ ScalarDev S, const double *__restric
     for (long long q = (long long)blockIdx.x * kRedThreads + threadIdx.x; q < nrav;
          q += (long long)gridDim.x * kRedThreads)
         // ny_grid > 0: (xr, yr) are the 1-D axes of an 'ij' grid; else the raveled meshgrid
-        acc += (ny_grid > 0) ? scalar_at(S, t, xr[q / ny_grid], yr[q % ny_grid]) : scalar_at(S, t, xr[q], yr[q]);
+        acc += (ny_grid > 0) ? scalar_at_k(S, k, t, xr[q / ny_grid], yr[q % ny_grid]) : scalar_at_k(S, k, t, xr[q], yr[q]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -136,7 +224,7 @@ lavd_kernel(const __grid_constant__ ScalarDev S, const double2 *__restrict__ fm_
         double2 p = __ldg(traj + k);
         if (period_x != 0.0) p.x = pymod_any(p.x, period_x);
         if (period_y != 0.0) p.y = pymod_any(p.y, period_y);
-        return fabs(scalar_at(S, __ldg(tspan + k), p.x, p.y) - __ldg(vavg + k));
+        return fabs(scalar_at_k(S, k, __ldg(tspan + k), p.x, p.y) - __ldg(vavg + k));
     };
     const double h = fabs(tspan[1] - tspan[0]);
     long long m = n - 1;  // number of intervals
@@ -265,12 +353,37 @@ void init_thomas_table() {
 
 }  // namespace
 
-ScalarDev make_scalar_dev(const FlowSpec &f) {
+ScalarDev make_scalar_dev(const FlowSpec &f, const VortSlabs *slabs) {
     ScalarDev S{};
     S.g = make_grid_dev(f);
     S.C = static_cast<const double *>(f.coef);
     S.linear = f.linear;
+    S.W = slabs ? slabs->W : nullptr;
+    S.wstride = slabs ? slabs->stride : 0;
     return S;
+}
+
+// The field contracted over time at the n output times: n slabs of one time level each.  Skipped
+// (W stays null, callers fall back to the 3-D evaluator) when the slabs would take more than a
+// quarter of the free device memory.
+VortSlabs build_vort_slabs(const FlowSpec &f, const double *tspan_dev, long long n, cudaStream_t s) {
+    VortSlabs V;
+    if (n <= 0 || n > 65535) return V;
+    if (std::getenv("B200CS_LAVD_NO_SLABS")) return V;   // A/B and test knob: the 64-tap 3-D evaluator everywhere
+    const ScalarDev S = make_scalar_dev(f, nullptr);
+    const long long slab = S.g.s0;   // elements of one time level, padded rows included
+    size_t free_b = 0, total_b = 0;
+    B2_CHECK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t bytes = (size_t)n * (size_t)slab * sizeof(double);
+    if (bytes > free_b / 4) return V;
+    V.mem = Scratch(bytes, s);
+    V.W = static_cast<const double *>(V.mem.ptr);
+    V.stride = slab;
+    long long nb = (slab + 255) / 256;
+    if (nb > 296) nb = 296;
+    vort_slab_kernel<<<dim3((unsigned)nb, (unsigned)n), 256, 0, s>>>(S, tspan_dev, slab, static_cast<double *>(V.mem.ptr));
+    B2_CHECK_CUDA(cudaGetLastError());
+    return V;
 }
 
 void launch_velocity_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s) {
@@ -299,10 +412,25 @@ void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, do
 }
 
 void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
-                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s) {
+                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s,
+                      const VortSlabs *slabs) {
     if (n <= 0) return;
     B2_REQUIRE(n <= 65535, "too many output times for the LAVD mean (%lld)", n);
-    const ScalarDev S = make_scalar_dev(f);
+    const ScalarDev S = make_scalar_dev(f, slabs);
+    if (S.W != nullptr && ny_grid > 0) {
+        // 'ij' grid of particles given by its axes xr[nrav / ny_grid], yr[ny_grid]: separable sums
+        const int pad = f.linear ? 0 : 2;
+        const int rows = f.grid.n[1] + pad, cols = f.grid.n[2] + pad;
+        Scratch wbuf(sizeof(double) * (size_t)(rows + cols), s);
+        double *wx = static_cast<double *>(wbuf.ptr), *wy = wx + rows;
+        axis_weights_kernel<<<(rows + 127) / 128, 128, 0, s>>>(S, 1, xr, nrav / ny_grid, rows, wx);
+        B2_CHECK_CUDA(cudaGetLastError());
+        axis_weights_kernel<<<(cols + 127) / 128, 128, 0, s>>>(S, 2, yr, ny_grid, cols, wy);
+        B2_CHECK_CUDA(cudaGetLastError());
+        slab_bilinear_kernel<<<(unsigned)n, 256, 0, s>>>(S.W, S.wstride, rows, cols, S.g.s1, wx, wy, sums);
+        B2_CHECK_CUDA(cudaGetLastError());
+        return;
+    }
     long long nb = (nrav + kRedThreads - 1) / kRedThreads;
     if (nb > 592) nb = 592;  // 4 blocks per SM on 148 SMs
     if (nb < 1) nb = 1;
@@ -317,10 +445,10 @@ void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const
 
 void launch_lavd(const FlowSpec &f, const double *fm_n, long long npts, long long n, const double *tspan,
                  const double *vavg, double period_x, double period_y, const uint8_t *mask, double *lavd,
-                 cudaStream_t s) {
+                 cudaStream_t s, const VortSlabs *slabs) {
     if (npts <= 0) return;
     B2_REQUIRE((reinterpret_cast<uintptr_t>(fm_n) & 15) == 0, "flowmap_n must be 16-byte aligned");
-    const ScalarDev S = make_scalar_dev(f);
+    const ScalarDev S = make_scalar_dev(f, slabs);
     lavd_kernel<<<(unsigned)((npts + 127) / 128), 128, 0, s>>>(
         S, reinterpret_cast<const double2 *>(fm_n), npts, n, tspan, vavg, period_x, period_y, mask, lavd);
     B2_CHECK_CUDA(cudaGetLastError());

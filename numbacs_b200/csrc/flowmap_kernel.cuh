@@ -365,7 +365,7 @@ struct LavdSink {
         double x = v[0], y = v[1];
         if (px != 0.0) x = pymod_any(x, px);
         if (py != 0.0) y = pymod_any(y, py);
-        const double f = fabs(scalar_at(*S, __ldg(tspan + k), x, y) - __ldg(vavg + k));
+        const double f = fabs(scalar_at_k(*S, k, __ldg(tspan + k), x, y) - __ldg(vavg + k));
         fl3 = fl2;
         fl2 = fl1;
         fl1 = f;

@@ -63,13 +63,21 @@ void launch_scalar_eval(const FlowSpec &f, const double *pts, long long npts, do
 void launch_velocity_eval(const FlowSpec &f, const double *pts, long long npts, double *out, cudaStream_t s);
 void launch_curl_tspan(const FlowSpec &f, const double *t, long long nt, const double *x, long long nx,
                        const double *y, long long ny, double h, double *curl, cudaStream_t s);
+// vorticity contracted over time at the LAVD output times (diag_kernels.cu); W == nullptr: not built
+struct VortSlabs {
+    Scratch mem;
+    const double *W = nullptr;
+    long long stride = 0;
+};
+VortSlabs build_vort_slabs(const FlowSpec &f, const double *tspan_dev, long long n, cudaStream_t s);
 void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const double *xr,
-                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s);
-ScalarDev make_scalar_dev(const FlowSpec &f);
+                      const double *yr, long long nrav, long long ny_grid, double *sums, cudaStream_t s,
+                      const VortSlabs *slabs = nullptr);
+ScalarDev make_scalar_dev(const FlowSpec &f, const VortSlabs *slabs = nullptr);
 void launch_lavd_flowmap(const FlowSpec &f, const IntegArgs &A, cudaStream_t s);
 void launch_lavd(const FlowSpec &f, const double *fm_n, long long npts, long long n, const double *tspan,
                  const double *vavg, double period_x, double period_y, const uint8_t *mask, double *lavd,
-                 cudaStream_t s);
+                 cudaStream_t s, const VortSlabs *slabs = nullptr);
 void launch_prefilter3(const double *data, long long n0, long long n1, long long n2, double *coefs,
                        cudaStream_t s);
 void launch_div_scalar(double *a, long long n, double d, cudaStream_t s);

@@ -319,15 +319,71 @@ __device__ __forceinline__ double eval_linear_s(const SplineGridDev &g, const do
     return v;
 }
 
-// a scalar field (vorticity): cubic-spline coefficients or the raw field for trilinear evaluation
+// The same two evaluators on a TIME-COLLAPSED slab W[m, n] = sum_a P0[a] C[i0 + a, m, n] (cubic) or
+// (1 - l0) F[i0] + l0 F[i0 + 1] (trilinear): LAVD evaluates the vorticity at the n output times
+// t_k only, the same for every particle, so the time contraction is done once per output time
+// (vort_slab_kernel, diag_kernels.cu) and each evaluation gathers 16 taps (4) instead of 64 (8).
+// The sum is the reference's nested t -> x -> y sum re-associated (t first): a rounding-level change.
+__device__ __forceinline__ double eval_spline_s2(const SplineGridDev &g, const double *__restrict__ W, double x,
+                                                 double y) {
+    if (!extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return 0.0;
+    int i1, i2;
+    double l1, l2;
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const bool lin = g.extrap == B200CS_EXTRAP_LINEAR;
+    double P1[4], P2[4];
+    bspline_weights(l1, lin, P1);
+    bspline_weights(l2, lin, P2);
+    const double *base = W + (long long)i1 * g.s1 + i2;
+    double acc1 = 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+        const double *c = base + b * g.s1;
+        const double acc2 =
+            sp_mad(P2[3], __ldg(c + 3), sp_mad(P2[2], __ldg(c + 2), sp_mad(P2[1], __ldg(c + 1), P2[0] * __ldg(c))));
+        acc1 = sp_mad(P1[b], acc2, acc1);
+    }
+    return acc1;
+}
+
+__device__ __forceinline__ double eval_linear_s2(const SplineGridDev &g, const double *__restrict__ W, double x,
+                                                 double y) {
+    if (!extrap_coord(g, 1, x) || !extrap_coord(g, 2, y)) return 0.0;
+    int i1, i2;
+    double l1, l2;
+    axis_locate(g, 1, x, i1, l1);
+    axis_locate(g, 2, y, i2, l2);
+    const double *c = W + (long long)i1 * g.s1 + i2;
+    double va = 0.0;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+        const double wb = b ? l1 : 1.0 - l1;
+        const double *cc = c + b * g.s1;
+        va = sp_mad(wb, sp_mad(l2, __ldg(cc + 1), (1.0 - l2) * __ldg(cc)), va);
+    }
+    return va;
+}
+
+// a scalar field (vorticity): cubic-spline coefficients or the raw field for trilinear evaluation;
+// W (optional): slabs collapsed at the output times, slab k at W + k * wstride (layout of one time
+// level of C: g.s1 elements per row)
 struct ScalarDev {
     SplineGridDev g;
     const double *C;
     int linear;
+    const double *W;
+    long long wstride;
 };
 
 __device__ __forceinline__ double scalar_at(const ScalarDev &S, double t, double x, double y) {
     return S.linear ? eval_linear_s(S.g, S.C, t, x, y) : eval_spline_s(S.g, S.C, t, x, y);
+}
+// the field at output time k (t == tspan[k]): from the collapsed slab when there is one
+__device__ __forceinline__ double scalar_at_k(const ScalarDev &S, long long k, double t, double x, double y) {
+    if (S.W == nullptr) return scalar_at(S, t, x, y);
+    const double *Wk = S.W + k * S.wstride;
+    return S.linear ? eval_linear_s2(S.g, Wk, x, y) : eval_spline_s2(S.g, Wk, x, y);
 }
 
 // Python float modulo (result takes the sign of the divisor), diagnostics.py:350-376
