@@ -372,10 +372,12 @@ VortSlabs build_vort_slabs(const FlowSpec &f, const double *tspan_dev, long long
     if (std::getenv("B200CS_LAVD_NO_SLABS")) return V;   // A/B and test knob: the 64-tap 3-D evaluator everywhere
     const ScalarDev S = make_scalar_dev(f, nullptr);
     const long long slab = S.g.s0;   // elements of one time level, padded rows included
-    size_t free_b = 0, total_b = 0;
-    B2_CHECK_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t bytes = (size_t)n * (size_t)slab * sizeof(double);
-    if (bytes > free_b / 4) return V;
+    if (bytes > ((size_t)2 << 30)) {   // small slab sets are simply taken from the stream's pool (cudaMemGetInfo is slow)
+        size_t free_b = 0, total_b = 0;
+        B2_CHECK_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes > free_b / 4) return V;
+    }
     V.mem = Scratch(bytes, s);
     V.W = static_cast<const double *>(V.mem.ptr);
     V.stride = slab;

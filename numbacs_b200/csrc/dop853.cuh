@@ -599,9 +599,9 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                         rc[6][i] = h * detail::dense_row<6, N>(K, i, std::make_integer_sequence<int, 16>{});
                         rc[7][i] = h * detail::dense_row<7, N>(K, i, std::make_integer_sequence<int, 16>{});
                     }
-                    do {
-                        const double th = (tnext - x) / h, th1 = 1.0 - th;
-                        double yo[N];
+                    // contd8 at the output time tq (Hairer's nested form)
+                    auto dense_at = [&](double tq, double (&yo)[N]) {
+                        const double th = (tq - x) / h, th1 = 1.0 - th;
 #pragma unroll
                         for (int i = 0; i < N; ++i) {
                             double v = th * rc[7][i];
@@ -613,6 +613,10 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                             v = th * (rc[1][i] + v);
                             yo[i] = rc[0][i] + v;
                         }
+                    };
+                    do {
+                        double yo[N];
+                        dense_at(tnext, yo);
                         sink(iout, yo);
                         ++iout;
                         tnext = t_out(iout);

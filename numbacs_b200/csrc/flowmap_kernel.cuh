@@ -361,17 +361,21 @@ struct LavdSink {
     int n;             // number of output times
     int m_simpson;     // number of intervals covered by the 1/3 rule: n-1 if even, n-2 if odd
     double f0, sum, fl1, fl2, fl3;  // first value, weighted interior sum, last three values
-    __device__ __forceinline__ void operator()(int k, const double (&v)[2]) {
+    // |vort(t_k, position) - mean_k|  (diagnostics.py:350-376)
+    __device__ __forceinline__ double integrand(int k, const double (&v)[2]) const {
         double x = v[0], y = v[1];
         if (px != 0.0) x = pymod_any(x, px);
         if (py != 0.0) y = pymod_any(y, py);
-        const double f = fabs(scalar_at_k(*S, k, __ldg(tspan + k), x, y) - __ldg(vavg + k));
+        return fabs(scalar_at_k(*S, k, __ldg(tspan + k), x, y) - __ldg(vavg + k));
+    }
+    __device__ __forceinline__ void accumulate(int k, double f) {
         fl3 = fl2;
         fl2 = fl1;
         fl1 = f;
         if (k == 0) f0 = f;
         else if (k < m_simpson) sum = fma((k & 1) ? 4.0 : 2.0, f, sum);
     }
+    __device__ __forceinline__ void operator()(int k, const double (&v)[2]) { accumulate(k, integrand(k, v)); }
     // composite Simpson (utils.py:611-655) with spacing h
     __device__ __forceinline__ double finish(double h) const {
         const int m = n - 1;
@@ -383,13 +387,22 @@ struct LavdSink {
 };
 
 // The fused LAVD kernel keeps 32 x 1 strips: its cost is the 64-tap VORTICITY gather at 601 output
-// times per particle, whose lanes coalesce along y (config 4: 32.2 ms with strips, 36.4 ms with 4 x 8
-// tiles, profiles/r3_configs_c1_c4.json / r3_configs_c1_c4_lavd_tile4.json).
+// times per particle, whose lanes coalesce along y (config 4 before the time-collapsed slabs: 32.2 ms
+// with strips, 36.4 ms with 4 x 8 tiles, profiles/r3_configs_c1_c4_before_slabs.json /
+// r3_configs_c1_c4_lavd_tile4.json).
 #ifndef B200CS_LAVD_TILE_I
 #define B200CS_LAVD_TILE_I 1
 #endif
+// Four blocks per SM (128 registers; the spills sit in the ~2 step attempts of a particle, not in
+// its 601 output evaluations): the kernel is bound by the latency of the per-output chain
+// (dense polynomial -> cell location -> 16 gathers -> Simpson), config 4: 21.3 ms at 168 registers /
+// three blocks, 14.6 at four, 15.6 at five; evaluating two output times per iteration for overlap
+// (254 registers) measured 20.6 / 15.5 and was dropped (profiles/r3_ab_lavd.txt).
+#ifndef B200CS_LAVD_MINBLOCKS
+#define B200CS_LAVD_MINBLOCKS 4
+#endif
 template <class Rhs>
-__global__ void __launch_bounds__(128) lavd_flowmap_kernel(const __grid_constant__ IntegArgs A) {
+__global__ void __launch_bounds__(128, B200CS_LAVD_MINBLOCKS) lavd_flowmap_kernel(const __grid_constant__ IntegArgs A) {
     static_assert(Rhs::N == 2, "LAVD is defined for 2-D flows");
     constexpr int kTI = B200CS_LAVD_TILE_I, kTJ = 32 / kTI;   // warp = kTI x kTJ tile of the grid (shape_tile_i)
     long long q = (long long)blockIdx.x * 128 + threadIdx.x;

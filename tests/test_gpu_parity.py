@@ -479,6 +479,56 @@ def test_lavd_cubic_spline(nb, oracle):
             assert np.abs(fm_end[~mask] - fmno[:, :, -1][~mask]).max() <= 1e-7
 
 
+@pytest.mark.parametrize("linear", [False, True])
+@pytest.mark.parametrize("mode", ["constant", "linear", "nearest"])
+def test_lavd_time_collapsed_vorticity(nb, mode, linear):
+    """The LAVD kernels evaluate the vorticity on slabs contracted over time at the output times (16 taps
+    instead of 64; spatial means of an 'ij' grid through per-axis weight sums).  That re-associates the
+    reference's t -> x -> y sum (flows.py:387-415 / 601-640 -> eval_spline / eval_linear): it must agree
+    with the plain 3-D evaluator (B200CS_LAVD_NO_SLABS=1) to rounding, for every extrapolation mode,
+    with particles and output times outside the vorticity grid, for the fused and the two-call path."""
+    import os
+    t, x, y, U, V = _dg_like_field(nt=17, nx=33, ny=25)
+    rng = np.random.default_rng(7)
+    T, X, Y = np.meshgrid(t, x, y, indexing="ij")
+    vort = np.sin(3 * X + 0.3 * T) * np.cos(2 * Y) + 0.1 * rng.normal(size=T.shape)
+    grid, Cu, Cv = nb.flows.get_interp_arrays_2D(t, x, y, U, V)
+    f = nb.flows.get_flow_2D(grid, Cu, Cv, extrap_mode="linear")
+    # the vorticity grid is SMALLER than the particle domain and the time span: the out-of-grid rules matter
+    tv, xv, yv = t[2:-3], x[4:-5], y[3:-4]
+    vv = vort[2:-3, 4:-5, 3:-4]
+    if linear:
+        w = nb.flows.get_callable_scalar_linear(((tv[0], tv[-1], len(tv)), (xv[0], xv[-1], len(xv)),
+                                                 (yv[0], yv[-1], len(yv))), vv, extrap_mode=mode)
+    else:
+        gw, Cw = nb.flows.get_interp_arrays_scalar(tv, xv, yv, vv)
+        w = nb.flows.get_callable_scalar(gw, Cw, extrap_mode=mode)
+    xg, yg = np.linspace(0.1, 1.9, 40), np.linspace(0.1, 0.9, 24)
+    Xg, Yg = np.meshgrid(xg, yg, indexing="ij")
+    mask = rng.random((40, 24)) < 0.1
+    one = np.array([1.0])
+    res = {}
+    for slabs in (True, False):
+        if slabs:
+            os.environ.pop("B200CS_LAVD_NO_SLABS", None)
+        else:
+            os.environ["B200CS_LAVD_NO_SLABS"] = "1"
+        try:
+            fused, ts = nb.diagnostics.lavd_flowmap_grid_2D(f, 1.0, 6.0, xg, yg, one, w, n=23, period_x=1.5,
+                                                            mask=mask)
+            fmn, ts2 = nb.integration.flowmap_n_grid_2D(f, 1.0, 6.0, xg, yg, one, n=23)
+            two = nb.diagnostics.lavd_grid_2D(fmn, ts2, 6.0, w, Xg.ravel(), Yg.ravel(), 1.5, 0.0, mask=mask)
+            sums = np.asarray(nb.diagnostics.lavd_vort_sums(w, ts2, Xg.ravel(), Yg.ravel()))
+        finally:
+            os.environ.pop("B200CS_LAVD_NO_SLABS", None)
+        res[slabs] = (np.asarray(fused), np.asarray(two), sums)
+    scale = max(1.0, np.abs(res[False][0]).max())
+    for a, b in zip(res[True], res[False]):
+        assert np.array_equal(a == 0.0, b == 0.0)
+        assert np.abs(a - b).max() <= 1e-12 * max(scale, np.abs(b).max())
+    assert np.abs(res[False][0]).max() > 0.0
+
+
 # ------------------------------------------------------------------ API behaviour / edge cases
 
 def test_unknown_funcptr_is_rejected(nb):
