@@ -208,7 +208,11 @@ B200CS_API int b200cs_lavd_grid_2d(const double *flowmap_n /*[nx,ny,n,2]*/, int6
  * accumulates the composite Simpson sum.  vort_avg (nullable [n]): precomputed spatial means;
  * when NULL they are computed over the (x, y) grid itself (diagnostics.py:324-331 with
  * xrav, yrav = meshgrid(x, y).ravel()).  flowmap_out (nullable [nx,ny,2]) receives the final
- * positions, tspan (nullable [n]) the output times params[0]*t_eval. */
+ * positions, tspan (nullable [n]) the output times params[0]*t_eval.
+ * The three LAVD entries evaluate the vorticity on slabs contracted over time at the n output times
+ * (n x one time level of the field in scratch memory, 16 taps per evaluation instead of 64; skipped
+ * when the slabs would not fit): the reference's t -> x -> y sum re-associated, a rounding-level
+ * change.  Environment B200CS_LAVD_NO_SLABS=1 selects the plain 3-D evaluator (tests, A/B). */
 B200CS_API int b200cs_lavd_flowmap_grid_2d(int flow, double t0, double T, const double *x, int64_t nx,
                                 const double *y, int64_t ny, const double *params, int nparams,
                                 int method, double rtol, double atol, const uint8_t *mask, int n,

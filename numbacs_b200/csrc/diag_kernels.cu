@@ -121,29 +121,39 @@ vort_slab_kernel(const __grid_constant__ ScalarDev S, const double *__restrict__
 
 // Spatial sums over an 'ij' grid of particles without touching a particle: the evaluator is a tensor
 // product, so  sum_ij f(x_i, y_j) = sum_m sum_n WX[m] W[m, n] WY[n]  with the blending weights of
-// all x_i (y_j) accumulated per coefficient row (column).  aw[m] = sum_i weight of point i on row m
-// of axis d, in ascending i (deterministic); the extrapolation rule of the axis is applied per point.
-__global__ void axis_weights_kernel(const __grid_constant__ ScalarDev S, int d, const double *__restrict__ pts,
-                                    long long npts, int rows, double *__restrict__ aw) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    if (m >= rows) return;
-    const bool lin = S.g.extrap == B200CS_EXTRAP_LINEAR;
-    double acc = 0.0;
-    for (long long i = 0; i < npts; ++i) {
-        double x = __ldg(pts + i);
-        if (!extrap_coord(S.g, d, x)) continue;
-        int i1;
+// all x_i (y_j) accumulated per coefficient row (column).  Two passes, both deterministic: every
+// point stores its first row and its (up to four) weights after the axis' extrapolation rule;
+// then one thread per row adds the weights of the points that touch it in ascending point order.
+__global__ void axis_point_weights_kernel(const __grid_constant__ ScalarDev S, int d, const double *__restrict__ pts,
+                                          long long npts, int *__restrict__ first, double *__restrict__ w4) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    double x = __ldg(pts + i);
+    double P[4] = {0.0, 0.0, 0.0, 0.0};
+    int i1 = -8;   // no row is within 4 of it: the point contributes nothing ('constant' mode, outside)
+    if (extrap_coord(S.g, d, x)) {
         double l;
         axis_locate(S.g, d, x, i1, l);
-        const int o = m - i1;
         if (S.linear) {
-            if (o == 0) acc += 1.0 - l;
-            else if (o == 1) acc += l;
-        } else if (o >= 0 && o < 4) {
-            double P[4];
-            bspline_weights(l, lin, P);
-            acc += (o == 0) ? P[0] : (o == 1) ? P[1] : (o == 2) ? P[2] : P[3];
+            P[0] = 1.0 - l;
+            P[1] = l;
+        } else {
+            bspline_weights(l, S.g.extrap == B200CS_EXTRAP_LINEAR, P);
         }
+    }
+    first[i] = i1;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) w4[4 * i + o] = P[o];
+}
+
+__global__ void axis_weights_kernel(const int *__restrict__ first, const double *__restrict__ w4, long long npts,
+                                    int rows, double *__restrict__ aw) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= rows) return;
+    double acc = 0.0;
+    for (long long i = 0; i < npts; ++i) {
+        const unsigned o = (unsigned)(m - __ldg(first + i));
+        if (o < 4u) acc += __ldg(w4 + 4 * i + o);
     }
     aw[m] = acc;
 }
@@ -423,11 +433,15 @@ void launch_vort_sums(const FlowSpec &f, const double *tspan, long long n, const
         // 'ij' grid of particles given by its axes xr[nrav / ny_grid], yr[ny_grid]: separable sums
         const int pad = f.linear ? 0 : 2;
         const int rows = f.grid.n[1] + pad, cols = f.grid.n[2] + pad;
-        Scratch wbuf(sizeof(double) * (size_t)(rows + cols), s);
-        double *wx = static_cast<double *>(wbuf.ptr), *wy = wx + rows;
-        axis_weights_kernel<<<(rows + 127) / 128, 128, 0, s>>>(S, 1, xr, nrav / ny_grid, rows, wx);
+        const long long npx = nrav / ny_grid, npy = ny_grid, npmax = npx > npy ? npx : npy;
+        Scratch wbuf(sizeof(double) * (size_t)(rows + cols + 4 * npmax) + sizeof(int) * (size_t)npmax, s);
+        double *wx = static_cast<double *>(wbuf.ptr), *wy = wx + rows, *w4 = wy + cols;
+        int *first = reinterpret_cast<int *>(w4 + 4 * npmax);
+        axis_point_weights_kernel<<<(unsigned)((npx + 127) / 128), 128, 0, s>>>(S, 1, xr, npx, first, w4);
+        axis_weights_kernel<<<(rows + 63) / 64, 64, 0, s>>>(first, w4, npx, rows, wx);
         B2_CHECK_CUDA(cudaGetLastError());
-        axis_weights_kernel<<<(cols + 127) / 128, 128, 0, s>>>(S, 2, yr, ny_grid, cols, wy);
+        axis_point_weights_kernel<<<(unsigned)((npy + 127) / 128), 128, 0, s>>>(S, 2, yr, npy, first, w4);
+        axis_weights_kernel<<<(cols + 63) / 64, 64, 0, s>>>(first, w4, npy, cols, wy);
         B2_CHECK_CUDA(cudaGetLastError());
         slab_bilinear_kernel<<<(unsigned)n, 256, 0, s>>>(S.W, S.wstride, rows, cols, S.g.s1, wx, wy, sums);
         B2_CHECK_CUDA(cudaGetLastError());

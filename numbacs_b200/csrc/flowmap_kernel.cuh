@@ -7,6 +7,8 @@
 // similar, and the final 16-byte stores are fully coalesced.
 // One translation unit per flow kind instantiates it (flowmap_<kind>.cu) so they build in parallel.
 #pragma once
+#include <atomic>
+
 #include "common.cuh"
 #include "dop853.cuh"
 #include "flows.cuh"
@@ -655,13 +657,17 @@ void launch_queue(const IntegArgs &A0, cudaStream_t s) {
     B2_CHECK_CUDA(cudaMemsetAsync(A.qcounter, 0, sizeof(unsigned long long), s));
     const long long init_blocks = (A.nq + 127) / 128;
     B2_REQUIRE(init_blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
-    static int resident = 0;   // blocks of the queue kernel the device holds at once
+    // blocks of the queue kernel the current device holds at once (cached per device)
+    static std::atomic<int> resident_of[64];
+    int dev = 0;
+    B2_CHECK_CUDA(cudaGetDevice(&dev));
+    int resident = (dev >= 0 && dev < 64) ? resident_of[dev].load(std::memory_order_relaxed) : 0;
     if (resident == 0) {
-        int dev = 0, sms = 0, per_sm = 0;
-        B2_CHECK_CUDA(cudaGetDevice(&dev));
+        int sms = 0, per_sm = 0;
         B2_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         B2_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, flowmap_queue_kernel<Rhs, MODE>, kBlock, 0));
         resident = sms * (per_sm > 0 ? per_sm : 1);
+        if (dev >= 0 && dev < 64) resident_of[dev].store(resident, std::memory_order_relaxed);
     }
     const long long want = (A.nq + kBlock - 1) / kBlock;
     const unsigned blocks = (unsigned)(want < resident ? want : resident);

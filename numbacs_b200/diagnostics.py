@@ -120,7 +120,9 @@ def lavd_flowmap_grid_2D(funcptr, t0, T, x, y, params, vort_interp, n=50, method
     """flowmap_n_grid_2D + lavd_grid_2D fused: the LAVD is accumulated along each trajectory while
     it is integrated, so the (nx, ny, n, 2) array is never stored.  Returns (lavd, tspan) or
     (lavd, tspan, final_flowmap).  Same result as the two reference calls
-    (integration.py:467-533, diagnostics.py:272-379) up to the order of the Simpson summation."""
+    (integration.py:467-533, diagnostics.py:272-379) up to the order of the Simpson summation.
+    The vorticity is evaluated on slabs contracted over time at the n output times (16 taps per
+    evaluation instead of 64; include/b200cs.h), the spatial means through per-axis weight sums."""
     if not isinstance(vort_interp, ScalarField):
         raise NotImplementedError("vort_interp must come from numbacs_b200.flows.get_callable_scalar(_linear)")
     xa, ya, pa, ma = _lib.arg_in(x), _lib.arg_in(y), _lib.arg_in(params), _lib.mask_in(mask)
