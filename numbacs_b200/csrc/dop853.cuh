@@ -108,6 +108,25 @@ struct StepCounts {
     int dense = 0;     // accepted steps that needed the three extra dense-output stages
 };
 
+// The controller's non-trivial literals in the constant bank (B200CS_CTL_CONSTS): a double that is not a
+// short immediate costs two UMOV per use on sm_100 (one per 32-bit half) and two uniform registers
+// that ptxas then lacks for the tableau: with these seven literals as LDCU.64 loads the
+// double-gyre attempt went from 293 to 243 non-FP64 instructions and from 62 bytes of spills to 4
+// (the uniform-register file had been overflowing into local memory and R2UR moves):
+// 1170.6 -> 1192.3 M points/s at 8192^2, bit-identical results (profiles/r3_ab_nonfp64.txt).
+struct __align__(16) CtlConsts {
+    double tenth, uround, one01, hundredth, safe, facmin, tiny, pad;
+};
+static __constant__ CtlConsts kCtl = {0.1, 2.3e-16, 1.01, 0.01, 0.9, 0.333, 1.0e-280, 0.0};
+#ifndef B200CS_CTL_CONSTS
+#define B200CS_CTL_CONSTS 1
+#endif
+#if B200CS_CTL_CONSTS
+#define B2_CTL(field, literal) (::b200cs::kCtl.field)
+#else
+#define B2_CTL(field, literal) (literal)
+#endif
+
 // Optional part of the RHS interface (detected, so the other flows need not mention it):
 //   Rhs::kAuxAffine     time_part_affine<M>(x, h, c[M], aux) evaluates the time-only part at the
 //                       times x + c_m h without forming them (the phase is affine in c_m).
@@ -465,8 +484,8 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         }
         if (alive) do {
         if (nstep > kNmax) { status = B200CS_ST_NMAX; alive = false; break; }
-        if (0.1 * fabs(h) <= fabs(x) * kURound) { status = B200CS_ST_HSMALL; alive = false; break; }
-        if ((x + 1.01 * h - xend) * posneg > 0.0) {
+        if (B2_CTL(tenth, 0.1) * fabs(h) <= fabs(x) * B2_CTL(uround, kURound)) { status = B200CS_ST_HSMALL; alive = false; break; }
+        if ((x + B2_CTL(one01, 1.01) * h - xend) * posneg > 0.0) {
             h = xend - x;
             last = true;
         }
@@ -539,7 +558,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
 #endif
             err = detail::mad(e5, e5, err);
         }
-        double deno = detail::mad(0.01, err2, err);
+        double deno = detail::mad(B2_CTL(hundredth, 0.01), err2, err);
         if (deno <= 0.0) deno = 1.0;
 #if B200CS_LEAN
         err = fabs(h) * err * rsqrt(deno * (double)N);
@@ -550,12 +569,12 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         // g = 0.9 err^(-1/8) = 1 / (fac11 / safe); err == 0 (or below the seed's range) -> +inf, i.e. the
         // growth clamp; a NaN err stays NaN and fmax / fmin then pick the 1/3 of a rejected step
 #if B200CS_CTRL_ONE_NEWTON
-        double g = kSafe * detail::inv_eighth_root1(err);
+        double g = B2_CTL(safe, kSafe) * detail::inv_eighth_root1(err);
 #else
         double g = kSafe * detail::inv_eighth_root(err);
 #endif
-        if (err <= 1.0e-280) g = __longlong_as_double(0x7ff0000000000000LL);
-        double hnew = h * fmin(1.0 / kFacc2, fmax(1.0 / kFacc1, g));
+        if (err <= B2_CTL(tiny, 1.0e-280)) g = __longlong_as_double(0x7ff0000000000000LL);
+        double hnew = h * fmin(1.0 / kFacc2, fmax(B2_CTL(facmin, 1.0 / kFacc1), g));
 #else
         const double fac11 = detail::pow_eighth(err);
 #if B200CS_LEAN2
@@ -636,7 +655,7 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
         } else {
             // ---- rejected
 #if B200CS_CTRL_FAST
-            hnew = h * fmax(1.0 / kFacc1, g);
+            hnew = h * fmax(B2_CTL(facmin, 1.0 / kFacc1), g);
 #else
             hnew = h / fmin(kFacc1, fac11s);
 #endif

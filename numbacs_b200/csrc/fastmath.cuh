@@ -58,9 +58,36 @@ static __device__ __noinline__ double2 sincos_slow(double x) {
     return r;
 }
 
+// Round 2, last session: the FP64 pipe of the integration kernels idles ~15 % of the time although
+// the FP64 instruction stream could fill it, and what moves the needle is the NON-FP64 issue slots
+// between them (profiles/r3_ab_nonfp64.txt, double gyre at 8192^2):
+//   B200CS_FLIP_ADD    the sign flip (-1)^k as ONE integer multiply-add on the high word
+//                      (k * 2^31 + hi: the carry leaves the word) instead of a shift and a LOP3:
+//                      320 -> 295 non-FP64 instructions per attempt, 1150.6 -> 1170.8 M points/s,
+//                      bit-identical;
+//   B200CS_FLIP_EARLY  the flip applied to r (the polynomial is odd) instead of to the result, so it
+//                      leaves the Horner chain's critical path.  Value 2 (default) keeps the final
+//                      product r * Q rounded on its own (__dmul_rn), exactly as when the integer flip
+//                      fenced it: bit-identical results.  Value 1 lets it contract with the sum that
+//                      follows (794 -> 782 FP64 instructions, no faster) -- and breaks the wall identity
+//                      S+ + S- == 0 of the double gyre (the unrounded product leaves a 1e-17 residue
+//                      where the rounded ones cancel), which moves wall particles' first step and
+//                      with it the float32 goldens: rejected.
+#ifndef B200CS_FLIP_ADD
+#define B200CS_FLIP_ADD 1
+#endif
+#ifndef B200CS_FLIP_EARLY
+#define B200CS_FLIP_EARLY 2
+#endif
 // flips the sign of d when bit is 1
 __device__ __forceinline__ double flip_sign(double d, int bit) {
+#if B200CS_FLIP_ADD
+    // adding 2^31 to the high word flips bit 31 (the carry leaves the word): one IMAD (bit * 2^31 + hi)
+    // instead of a shift and a LOP3
+    return __hiloint2double((int)((unsigned)__double2hiint(d) + ((unsigned)bit << 31)), __double2loint(d));
+#else
     return __hiloint2double(__double2hiint(d) ^ (bit << 31), __double2loint(d));
+#endif
 }
 
 // r = x - k pi/2 with k = rint(x 2/pi) (|x| < 1e5); q = k mod 2^32
@@ -271,6 +298,9 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
         const double t = u[m] + kWide.magic;
         q[m] = __double2loint(t);
         r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+#if B200CS_FLIP_EARLY
+        r[m] = flip_sign(r[m], q[m] & 1);  // (-1)^k on r: the polynomial is odd, the bits of the result are the same
+#endif
         z[m] = r[m] * r[m];
         p[m] = kWide.cp[7];
     }
@@ -281,7 +311,15 @@ __device__ __forceinline__ void sinpi12_v(const double (&u)[M], double (&s)[M]) 
 #pragma unroll
         for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], kWide.cp[k]);
 #pragma unroll
-    for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], kWide.pi_hi), q[m] & 1);
+    for (int m = 0; m < M; ++m) {
+#if B200CS_FLIP_EARLY == 2
+        s[m] = __dmul_rn(r[m], fma(p[m], z[m], kWide.pi_hi));   // rounded on its own, as when the flip followed it
+#elif B200CS_FLIP_EARLY
+        s[m] = r[m] * fma(p[m], z[m], kWide.pi_hi);
+#else
+        s[m] = flip_sign(r[m] * fma(p[m], z[m], kWide.pi_hi), q[m] & 1);
+#endif
+    }
 }
 
 // amp * sin(pi u) with the amplitude folded into the coefficients: ce = amp * {cp0 .. cp7, pi}
@@ -308,6 +346,9 @@ __device__ __forceinline__ void sinpi12_scaled_v(const double (&u)[M], double (&
         const double t = u[m] + kWide.magic;
         q[m] = __double2loint(t);
         r[m] = u[m] - (t - kWide.magic);  // exact, |r| <= 1/2
+#if B200CS_FLIP_EARLY
+        r[m] = flip_sign(r[m], q[m] & 1);
+#endif
         z[m] = r[m] * r[m];
         p[m] = ce[7];
     }
@@ -316,7 +357,15 @@ __device__ __forceinline__ void sinpi12_scaled_v(const double (&u)[M], double (&
 #pragma unroll
         for (int m = 0; m < M; ++m) p[m] = fma(p[m], z[m], ce[k]);
 #pragma unroll
-    for (int m = 0; m < M; ++m) s[m] = flip_sign(r[m] * fma(p[m], z[m], ce[8]), q[m] & 1);
+    for (int m = 0; m < M; ++m) {
+#if B200CS_FLIP_EARLY == 2
+        s[m] = __dmul_rn(r[m], fma(p[m], z[m], ce[8]));   // rounded on its own, as when the flip followed it
+#elif B200CS_FLIP_EARLY
+        s[m] = r[m] * fma(p[m], z[m], ce[8]);
+#else
+        s[m] = flip_sign(r[m] * fma(p[m], z[m], ce[8]), q[m] & 1);
+#endif
+    }
 }
 
 // (A branch-free form -- no libm fall-back, r forced to 0 for finite |u| >= 2^51 so that a whole step
