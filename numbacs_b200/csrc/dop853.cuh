@@ -87,6 +87,14 @@
 #ifndef B200CS_QSYNC_EVERY
 #define B200CS_QSYNC_EVERY 3   // every 2 / 3 / 4 attempts: 321.6 / 325.4 / 325.7 (config 2), 362.8 / 366.9 / 359.5 M points/s (10.8 M particles)
 #endif
+// B200CS_LEAN_TAIL: fewer issue slots in the accept / reject tail, results bit-identical
+// (profiles/r3_ab_nonfp64.txt): 1 = the first-same-as-last slope is evaluated straight into K[1] in the
+// final-time kernels and the last step leaves through the common exit (no early break: fewer
+// merge copies), 245 -> 234 non-FP64 instructions, 1182.8 -> 1190.6 M points/s at 8192^2;
+// 2 = also max(|y|, |y5|) as compare + select instead of fmax with its NaN fix-up: 223, 1193.7.
+#ifndef B200CS_LEAN_TAIL
+#define B200CS_LEAN_TAIL 2
+#endif
 #ifndef B200CS_FSAL_ALWAYS
 #define B200CS_FSAL_ALWAYS 0
 #endif
@@ -525,7 +533,14 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             s = detail::mad(dop::kTab.b[11], K[11][i], s);
             s = detail::mad(dop::kTab.b[12], K[12][i], s);
             y5[i] = detail::mad(h, s, y[i]);
+#if B200CS_LEAN_TAIL >= 2
+            // max(|y|, |y5|) as one compare and a select (fmax's NaN fix-up is an extra instruction; a NaN
+            // y5 is ignored here exactly as fmax ignores it, and err is NaN through e5 then anyway)
+            const double ay = fabs(y[i]), ay5 = fabs(y5[i]);
+            const double sk = detail::mad(rtol, ay5 > ay ? ay5 : ay, atol);
+#else
             const double sk = detail::mad(rtol, fmax(fabs(y[i]), fabs(y5[i])), atol);
+#endif
             double e3 = detail::mad(-dop::kTab.bhh[0], K[1][i], s);
             e3 = detail::mad(-dop::kTab.bhh[1], K[9][i], e3);
             e3 = detail::mad(-dop::kTab.bhh[2], K[12][i], e3);
@@ -592,7 +607,13 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             // ---- accepted
             ++cnt.accepted;
 #if !B200CS_FSAL_ALWAYS
+#if B200CS_LEAN_TAIL
+            // final-time kernels: the first-same-as-last slope goes straight into K[1] (nothing reads the
+            // old one any more; only the dense-output coefficients need both)
+            detail::eval_to(rhs, aux[12], xph, y5, K, DENSE ? 13 : 1);
+#else
             detail::eval_to(rhs, aux[12], xph, y5, K, 13);  // first-same-as-last slope, same time as stage 12
+#endif
 #endif
             if (DENSE) {
                 if (iout < n_out - 1 && (tnext - xph) * posneg <= 0.0) {
@@ -644,11 +665,19 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
             }
 #pragma unroll
             for (int i = 0; i < N; ++i) {
+#if B200CS_LEAN_TAIL
+                if (DENSE) K[1][i] = K[13][i];
+#else
                 K[1][i] = K[13][i];
+#endif
                 y[i] = y5[i];
             }
             x = xph;
+#if B200CS_LEAN_TAIL
+            alive = !last;   // one way out of the attempt: the step size below is simply not used any more
+#else
             if (last) { alive = false; break; }
+#endif
             if (fabs(hnew) > hmax) hnew = posneg * hmax;
             if (reject) hnew = posneg * fmin(fabs(hnew), fabs(h));
             reject = false;
