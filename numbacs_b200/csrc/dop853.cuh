@@ -95,6 +95,9 @@
 #ifndef B200CS_LEAN_TAIL
 #define B200CS_LEAN_TAIL 2
 #endif
+// (Measured on top and dropped, profiles/r3_ab_nonfp64.txt: the step-size clamps as compare + select, +-0;
+// the rsqrt of the error norm without libdevice's range test and slow-path call -- ptxas answers the
+// merged basic block with 28 bytes of spills inside the loop: 1195 -> 1114 M points/s.)
 #ifndef B200CS_FSAL_ALWAYS
 #define B200CS_FSAL_ALWAYS 0
 #endif
