@@ -98,6 +98,9 @@
 // (Measured on top and dropped, profiles/r3_ab_nonfp64.txt: the step-size clamps as compare + select, +-0;
 // the rsqrt of the error norm without libdevice's range test and slow-path call -- ptxas answers the
 // merged basic block with 28 bytes of spills inside the loop: 1195 -> 1114 M points/s.)
+#ifndef B200CS_DENSE_RCP   // A/B: theta of the dense output as (t - x) * (1/h)
+#define B200CS_DENSE_RCP 0
+#endif
 #ifndef B200CS_FSAL_ALWAYS
 #define B200CS_FSAL_ALWAYS 0
 #endif
@@ -643,8 +646,15 @@ __device__ __forceinline__ int dop853_integrate(const Rhs &rhs, bool active, dou
                         rc[7][i] = h * detail::dense_row<7, N>(K, i, std::make_integer_sequence<int, 16>{});
                     }
                     // contd8 at the output time tq (Hairer's nested form)
+#if B200CS_DENSE_RCP
+                    const double rh = 1.0 / h;   // one division per step instead of one per output row
+#endif
                     auto dense_at = [&](double tq, double (&yo)[N]) {
+#if B200CS_DENSE_RCP
+                        const double th = (tq - x) * rh, th1 = 1.0 - th;
+#else
                         const double th = (tq - x) / h, th1 = 1.0 - th;
+#endif
 #pragma unroll
                         for (int i = 0; i < N; ++i) {
                             double v = th * rc[7][i];
