@@ -1,5 +1,5 @@
 """Shared pieces of the at-size parity tests (tests/test_gpu_parity_atsize.py), the calibration tool
-(tools/parity_floor.py) and bench.py's parity block: the BASELINE configurations' synthetic inputs
+(tests/perf/parity_floor.py) and bench.py's parity block: the BASELINE configurations' synthetic inputs
  and the flow-map comparison.
 
 The comparison follows SURVEY section 8(d) "Parity gates": positions max|dx| <= 1e-8 x L over particles

@@ -11,14 +11,14 @@ sample stated (config 4 additionally because the reference materialises the [nx,
 array: 10 GB at full size).  The spline coefficients of configs 3 and 4 are prefiltered on the GPU by
 numbacs_b200 (setup, not part of the timed path) and handed to the reference's get_flow_2D as arrays.
 
-    python tools/cpu_configs.py > gpurun_out/cpu_configs.json        (needs a GPU only for that setup)
+    python tests/perf/cpu_configs.py > gpurun_out/cpu_configs.json        (needs a GPU only for that setup)
 """
 import json
 import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Parity at BASELINE sizes, product build and parity-calibration (strict) build side by side.
 
-    python tools/parity_floor.py [c1 c2 c3 c5 small] > gpurun_out/parity_floor.json
+    python tests/perf/parity_floor.py [c1 c2 c3 c5 small] > gpurun_out/parity_floor.json
 
 For each configuration the same particles are integrated by (a) the CPU oracle, (b) the product
 library libb200cs.so, (c) libb200cs_strict.so (B200CS_STRICT: reference evaluation order,
@@ -14,7 +14,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np

@@ -7,7 +7,7 @@ Three integrations of the same particles are compared in every test:
            reference's evaluation order, every operation rounded separately, CUDA libm.
 strict-vs-oracle differs ONLY by the two libms (<= 1-2 ulp each) -- no GPU implementation can be
 closer to the reference than that, so it is the measured floor.  Measured on B200
-(profiles/r2_parity_floor.json, tools/parity_floor.py):
+(profiles/r2_parity_floor.json, tests/perf/parity_floor.py):
   * double gyre (C1 full grid, C5 rows) and the MERRA-shaped spline flow (C3 full grid): product
     AND strict meet the north-star gate max|dx| <= 1e-8 x L on step-matching particles
     (C1 1.9e-9 vs 8.5e-11, C5 rows 8.0e-10 vs 1.2e-10, C3 1.8e-13 vs 5.4e-14), so the gate is the
