@@ -356,6 +356,10 @@ flowmap_kernel(const __grid_constant__ IntegArgs A) {
 // materialising the [nx, ny, n, 2] trajectory array (10 GB at config 4): the dense-output sink
 // evaluates |vort(t_k, traj(t_k)) - vort_avg[k]| as row k is produced and accumulates the composite
 // Simpson sum on the fly (the three last integrand values are kept for the odd-interval rule).
+// VK = 1: the vorticity is a cubic spline with time-collapsed slabs (what get_callable_scalar fields
+// always are when the slabs fit): the evaluator is called directly, the trilinear / 3-D variants and
+// their run-time switches are not in the loop.  VK = 0: anything (scalar_at_k decides per call).
+template <int VK>
 struct LavdSink {
     const ScalarDev *S;
     const double *tspan, *vavg;
@@ -368,7 +372,8 @@ struct LavdSink {
         double x = v[0], y = v[1];
         if (px != 0.0) x = pymod_any(x, px);
         if (py != 0.0) y = pymod_any(y, py);
-        return fabs(scalar_at_k(*S, k, __ldg(tspan + k), x, y) - __ldg(vavg + k));
+        if constexpr (VK == 1) return fabs(eval_spline_s2(S->g, S->W + (long long)k * S->wstride, x, y) - __ldg(vavg + k));
+        else return fabs(scalar_at_k(*S, k, __ldg(tspan + k), x, y) - __ldg(vavg + k));
     }
     __device__ __forceinline__ void accumulate(int k, double f) {
         fl3 = fl2;
@@ -400,10 +405,15 @@ struct LavdSink {
 // (dense polynomial -> cell location -> 16 gathers -> Simpson), config 4: 21.3 ms at 168 registers /
 // three blocks, 14.6 at four, 15.6 at five; evaluating two output times per iteration for overlap
 // (254 registers) measured 20.6 / 15.5 and was dropped (profiles/r3_ab_lavd.txt).
+// A second instantiation of the fused LAVD kernel for cubic-spline vorticity on time-collapsed slabs
+// (VK = 1 below): config 4 13.6 -> 13.1 ms (profiles/r3_ab_lavd.txt), results identical.
+#ifndef B200CS_LAVD_SPECIALIZE
+#define B200CS_LAVD_SPECIALIZE 1
+#endif
 #ifndef B200CS_LAVD_MINBLOCKS
 #define B200CS_LAVD_MINBLOCKS 4
 #endif
-template <class Rhs>
+template <class Rhs, int VK>
 __global__ void __launch_bounds__(128, B200CS_LAVD_MINBLOCKS) lavd_flowmap_kernel(const __grid_constant__ IntegArgs A) {
     static_assert(Rhs::N == 2, "LAVD is defined for 2-D flows");
     constexpr int kTI = B200CS_LAVD_TILE_I, kTJ = 32 / kTI;   // warp = kTI x kTJ tile of the grid (shape_tile_i)
@@ -428,7 +438,7 @@ __global__ void __launch_bounds__(128, B200CS_LAVD_MINBLOCKS) lavd_flowmap_kerne
         y[0] = A.x[i];
         y[1] = A.y[j];
         const int m = A.n_out - 1;
-        LavdSink sink{&A.vort, A.tspan_phys, A.vort_avg, A.period_x, A.period_y, A.n_out,
+        LavdSink<VK> sink{&A.vort, A.tspan_phys, A.vort_avg, A.period_x, A.period_y, A.n_out,
                       (m & 1) ? m - 1 : m, 0.0, 0.0, 0.0, 0.0, 0.0};
         sink(0, y);
         const Rhs rhs(A.rhs);
@@ -463,7 +473,11 @@ void launch_lavd_one(const IntegArgs &A, cudaStream_t s) {
     const long long blocks = A.npts > 0 ? (threads + 127) / 128 : 0;
     if (blocks <= 0) return;
     B2_REQUIRE(blocks < 2147483647LL, "too many particles for one launch (%lld)", A.npts);
-    lavd_flowmap_kernel<Rhs><<<(unsigned)blocks, 128, 0, s>>>(A);
+#if B200CS_LAVD_SPECIALIZE
+    if (A.vort.W != nullptr && !A.vort.linear) lavd_flowmap_kernel<Rhs, 1><<<(unsigned)blocks, 128, 0, s>>>(A);
+    else
+#endif
+    lavd_flowmap_kernel<Rhs, 0><<<(unsigned)blocks, 128, 0, s>>>(A);
     B2_CHECK_CUDA(cudaGetLastError());
 }
 
